@@ -1,0 +1,256 @@
+// C ABI of openvo_b200 (include/openvo_b200.h): context, workspace carving and the per-seam entry points.
+#include <cstdarg>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "../../include/openvo_b200.h"
+#include "common.cuh"
+
+namespace ovo {
+
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// defined in orb.cu / match.cu
+void orb_make_resize_tables(const OrbDims& d, int32_t* tab, int* tab_off, int* total);
+int orb_phase1_launch(const OrbDims& d, const OrbWorkspace* ws0, size_t ws_stride, const int32_t* tab_dev, const int* tab_off, int nb,
+                      const uint8_t* img, int pitch, size_t frame_stride, const uint8_t* mask, int mask_pitch,
+                      size_t mask_frame_stride, cudaStream_t st);
+int orb_phase2_launch(const OrbDims& d, const OrbWorkspace* ws0, size_t ws_stride, int nb, int max_sel, const int32_t* n_sel_dev,
+                      float* kp_out, uint8_t* desc_out, cudaStream_t st);
+int reproject_launch(const float* disp, int pitch, int cw, int ch, int x0, int y0, const double* Q16, float* xyz, cudaStream_t st);
+int disp_post_launch(const int16_t* disp, int W, int H, int x0, int y0, int cw, int ch, float lo, float hi, float* disp_f32,
+                     uint8_t* mask, int nb, cudaStream_t st);
+int crop_launch(const uint8_t* img, int pitch, size_t frame_stride, int x0, int y0, int cw, int ch, int nb, uint8_t* out, cudaStream_t st);
+
+struct Layout {
+    SgbmDims sg;
+    OrbDims orb;
+    int x0, y0, cw, ch;
+    size_t sgbm_bytes, orb_bytes, frame_bytes;  // per frame
+    size_t tab_bytes, knn_bytes, nsel_bytes, total;
+    int tab_off[2 * ORB_NLEVELS], tab_total;
+};
+
+static int make_layout(const ovo_config* c, Layout* L) {
+    if (!c) { set_error("null config"); return 1; }
+    const ovo_sgbm_params& p = c->sgbm;
+    if (c->width <= 0 || c->height <= 0 || c->max_batch < 1) { set_error("bad image size / batch"); return 1; }
+    if (p.minDisparity != 0) { set_error("minDisparity != 0 is outside the pinned SGBM domain (SURVEY.md A.4)"); return 1; }
+    if (p.numDisparities <= 0 || p.numDisparities % 16 || p.numDisparities > 256) { set_error("numDisparities must be a multiple of 16 in [16, 256]"); return 1; }
+    if (c->width <= p.numDisparities) { set_error("image narrower than the disparity range"); return 1; }
+    if (p.blockSize < 3 || p.blockSize > 11 || !(p.blockSize & 1)) { set_error("blockSize must be odd in [3, 11]"); return 1; }
+    SgbmDims& s = L->sg;
+    s.W = c->width; s.H = c->height; s.D = p.numDisparities;
+    s.Dp = s.D <= 64 ? 64 : (s.D <= 128 ? 128 : 256);
+    s.W1 = s.W - s.D; s.bs = p.blockSize; s.P1 = p.P1;
+    s.P2 = p.P2 > p.P1 + 1 ? p.P2 : p.P1 + 1;
+    s.uniq = p.uniquenessRatio;
+    s.disp12 = p.disp12MaxDiff > 0 ? p.disp12MaxDiff : 1;
+    s.ftzero = (p.preFilterCap > 15 ? p.preFilterCap : 15) | 1;
+    s.speckleWin = p.speckleWindowSize; s.speckleDiff = 16 * p.speckleRange;
+    if (s.ftzero > 127) { set_error("preFilterCap too large"); return 1; }
+    if (s.P1 < 0 || s.bs * s.bs * (2 * s.ftzero + 63) + s.P2 > 32767) {
+        set_error("SGBM parameters leave the int16 cost domain OpenCV's result is pinned for (SURVEY.md A.4 validity domain)");
+        return 1;
+    }
+    // reference slice semantics (bug-compatible B1): img[roi[1]:roi[3], roi[0]:roi[2]] with numpy clamping
+    auto clampi = [](int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); };
+    auto norm = [&](int v, int n) { return clampi(v < 0 ? v + n : v, 0, n); };
+    const int y0 = norm(c->roi[1], s.H), y1 = norm(c->roi[3], s.H), x0 = norm(c->roi[0], s.W), x1 = norm(c->roi[2], s.W);
+    L->x0 = x0; L->y0 = y0; L->cw = x1 > x0 ? x1 - x0 : 0; L->ch = y1 > y0 ? y1 - y0 : 0;
+    if (L->cw < 16 || L->ch < 16) { set_error("cropped frame %dx%d too small", L->cw, L->ch); return 1; }
+    if (c->nfeatures < 1) { set_error("nfeatures must be positive"); return 1; }
+    orb_make_dims(L->cw, L->ch, c->nfeatures, &L->orb);
+    L->sgbm_bytes = sgbm_workspace_bytes(s);
+    L->orb_bytes = align_up(orb_workspace_bytes(L->orb), 256);
+    L->frame_bytes = L->sgbm_bytes + L->orb_bytes;
+    orb_make_resize_tables(L->orb, nullptr, L->tab_off, &L->tab_total);
+    L->tab_bytes = align_up((size_t)L->tab_total * 4, 256);
+    L->knn_bytes = align_up(knn2_scratch_bytes(L->orb.kp_cap, L->orb.kp_cap), 256);
+    L->nsel_bytes = align_up((size_t)c->max_batch * 4, 256);
+    L->total = L->frame_bytes * c->max_batch + L->tab_bytes + L->knn_bytes + L->nsel_bytes + 256;
+    return 0;
+}
+
+}  // namespace ovo
+
+using namespace ovo;
+
+struct ovo_ctx {
+    ovo_config cfg;
+    Layout L;
+    uint8_t* base;
+    SgbmWorkspace sg0;
+    OrbWorkspace orb0;
+    int32_t* tab_dev;
+    uint32_t* knn_scratch;
+    int32_t* nsel_dev;
+    // pinned host staging for the keypoint selection
+    int32_t* h_lvl;    // [max_batch][32]
+    float* h_resp;     // [max_batch][cand_cap][2]
+    int32_t* h_sel;    // [max_batch][kp_cap]
+    int32_t* h_nsel;   // [max_batch]
+};
+
+extern "C" {
+
+const char* ovo_last_error(void) { return g_err; }
+int ovo_abi_version(void) { return OVO_ABI_VERSION; }
+
+int ovo_cropped_size(const ovo_config* cfg, int* cw, int* ch) {
+    Layout L;
+    if (make_layout(cfg, &L)) return 1;
+    *cw = L.cw; *ch = L.ch;
+    return 0;
+}
+
+int ovo_kp_capacity(const ovo_config* cfg) {
+    Layout L;
+    if (make_layout(cfg, &L)) return -1;
+    return L.orb.kp_cap;
+}
+
+size_t ovo_workspace_bytes(const ovo_config* cfg) {
+    Layout L;
+    if (make_layout(cfg, &L)) return 0;
+    return L.total;
+}
+
+ovo_ctx* ovo_create(const ovo_config* cfg, void* workspace_dev, size_t workspace_bytes) {
+    Layout L;
+    if (make_layout(cfg, &L)) return nullptr;
+    if (!workspace_dev || workspace_bytes < L.total || ((uintptr_t)workspace_dev & 255)) {
+        set_error("workspace must be 256-byte aligned and at least %zu bytes", L.total);
+        return nullptr;
+    }
+    ovo_ctx* c = new ovo_ctx();
+    c->cfg = *cfg; c->L = L; c->base = (uint8_t*)workspace_dev;
+    sgbm_carve(L.sg, c->base, &c->sg0);
+    orb_carve(L.orb, c->base + L.sgbm_bytes, &c->orb0);
+    uint8_t* p = c->base + L.frame_bytes * cfg->max_batch;
+    c->tab_dev = (int32_t*)p; p += L.tab_bytes;
+    c->knn_scratch = (uint32_t*)p; p += L.knn_bytes;
+    c->nsel_dev = (int32_t*)p;
+    std::vector<int32_t> tab(L.tab_total);
+    int tot;
+    orb_make_resize_tables(L.orb, tab.data(), c->L.tab_off, &tot);
+    bool ok = cudaMemcpy(c->tab_dev, tab.data(), (size_t)tot * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+    const int nb = cfg->max_batch;
+    ok = ok && cudaMallocHost((void**)&c->h_lvl, (size_t)nb * 32 * 4) == cudaSuccess;
+    ok = ok && cudaMallocHost((void**)&c->h_resp, (size_t)nb * L.orb.cand_cap * 8) == cudaSuccess;
+    ok = ok && cudaMallocHost((void**)&c->h_sel, (size_t)nb * L.orb.kp_cap * 4) == cudaSuccess;
+    ok = ok && cudaMallocHost((void**)&c->h_nsel, (size_t)nb * 4) == cudaSuccess;
+    if (!ok) {
+        set_error("ovo_create: CUDA failure while staging tables (%s)", cudaGetErrorString(cudaGetLastError()));
+        delete c;
+        return nullptr;
+    }
+    return c;
+}
+
+void ovo_destroy(ovo_ctx* c) {
+    if (!c) return;
+    cudaFreeHost(c->h_lvl); cudaFreeHost(c->h_resp); cudaFreeHost(c->h_sel); cudaFreeHost(c->h_nsel);
+    delete c;
+}
+
+#define CHECK_CTX(c, nb)                                                            \
+    if (!(c)) { set_error("null context"); return 1; }                              \
+    if ((nb) < 1 || (nb) > (c)->cfg.max_batch) { set_error("batch %d outside [1, %d]", (nb), (c)->cfg.max_batch); return 1; }
+
+int ovo_sgbm_compute(ovo_ctx* c, const uint8_t* left, const uint8_t* right, int pitch, size_t frame_stride, int nb, int16_t* disp,
+                     void* stream) {
+    CHECK_CTX(c, nb);
+    if (pitch < c->L.sg.W) { set_error("pitch < width"); return 1; }
+    // the per-frame stride of the SGBM workspace is the whole frame block
+    return sgbm_launch(c->L.sg, &c->sg0, c->L.frame_bytes, nb, left, right, pitch, frame_stride, disp, (cudaStream_t)stream);
+}
+
+int ovo_disparity_post(ovo_ctx* c, const int16_t* disp, int nb, float* disp_f32, uint8_t* mask, void* stream) {
+    CHECK_CTX(c, nb);
+    return disp_post_launch(disp, c->L.sg.W, c->L.sg.H, c->L.x0, c->L.y0, c->L.cw, c->L.ch, c->cfg.min_valid_disparity,
+                            c->cfg.max_valid_disparity, disp_f32, mask, nb, (cudaStream_t)stream);
+}
+
+int ovo_crop_left(ovo_ctx* c, const uint8_t* img, int pitch, size_t frame_stride, int nb, uint8_t* out, void* stream) {
+    CHECK_CTX(c, nb);
+    return crop_launch(img, pitch, frame_stride, c->L.x0, c->L.y0, c->L.cw, c->L.ch, nb, out, (cudaStream_t)stream);
+}
+
+int ovo_reproject_3d(ovo_ctx* c, const float* disp_f32, float* xyz, void* stream) {
+    CHECK_CTX(c, 1);
+    return reproject_launch(disp_f32, c->L.cw, c->L.cw, c->L.ch, c->L.x0, c->L.y0, c->cfg.Q, xyz, (cudaStream_t)stream);
+}
+
+int ovo_orb_detect_compute(ovo_ctx* c, const uint8_t* img, const uint8_t* mask, int nb, float* kp, uint8_t* desc, int* n_kp_host,
+                           void* stream) {
+    CHECK_CTX(c, nb);
+    cudaStream_t st = (cudaStream_t)stream;
+    const Layout& L = c->L;
+    const OrbDims& d = L.orb;
+    const size_t fs = (size_t)L.cw * L.ch;
+    if (orb_phase1_launch(d, &c->orb0, L.frame_bytes, c->tab_dev, L.tab_off, nb, img, L.cw, fs, mask, L.cw, fs, st)) return 1;
+    for (int f = 0; f < nb; f++)
+        OVO_CUDA(cudaMemcpyAsync(c->h_lvl + 32 * f, (uint8_t*)c->orb0.lvl_count + L.frame_bytes * f, 17 * 4, cudaMemcpyDeviceToHost, st));
+    OVO_CUDA(cudaStreamSynchronize(st));
+    for (int f = 0; f < nb; f++) {
+        const int total = c->h_lvl[32 * f + 16];
+        if (total > d.cand_cap) { set_error("ORB candidate overflow (%d > %d)", total, d.cand_cap); return 1; }
+        if (total > 0)
+            OVO_CUDA(cudaMemcpyAsync(c->h_resp + (size_t)f * d.cand_cap * 2, (uint8_t*)c->orb0.cand_resp + L.frame_bytes * f,
+                                     (size_t)total * 8, cudaMemcpyDeviceToHost, st));
+    }
+    OVO_CUDA(cudaStreamSynchronize(st));
+    // retainBest x2 per level on the host (DESIGN.md "retainBest"); frames are independent -> one thread each
+    auto select_one = [&](int f) {
+        c->h_nsel[f] = orb_host_select(d, c->h_lvl + 32 * f, c->h_resp + (size_t)f * d.cand_cap * 2, c->h_sel + (size_t)f * d.kp_cap);
+    };
+    if (nb == 1) select_one(0);
+    else {
+        std::vector<std::thread> th;
+        const int nth = nb < 16 ? nb : 16;
+        for (int t = 0; t < nth; t++)
+            th.emplace_back([&, t] { for (int f = t; f < nb; f += nth) select_one(f); });
+        for (auto& x : th) x.join();
+    }
+    int max_sel = 0;
+    for (int f = 0; f < nb; f++) {
+        if (c->h_nsel[f] < 0) { set_error("ORB keypoint capacity exceeded (ties at the retainBest boundary)"); return 1; }
+        n_kp_host[f] = c->h_nsel[f];
+        max_sel = c->h_nsel[f] > max_sel ? c->h_nsel[f] : max_sel;
+        if (c->h_nsel[f] > 0)
+            OVO_CUDA(cudaMemcpyAsync((uint8_t*)c->orb0.sel + L.frame_bytes * f, c->h_sel + (size_t)f * d.kp_cap, (size_t)c->h_nsel[f] * 4,
+                                     cudaMemcpyHostToDevice, st));
+    }
+    OVO_CUDA(cudaMemcpyAsync(c->nsel_dev, c->h_nsel, (size_t)nb * 4, cudaMemcpyHostToDevice, st));
+    return orb_phase2_launch(d, &c->orb0, L.frame_bytes, nb, max_sel, c->nsel_dev, kp, desc, st);
+}
+
+int ovo_knn2_hamming(ovo_ctx* c, const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* nn, void* stream) {
+    CHECK_CTX(c, 1);
+    if (nq > c->L.orb.kp_cap || nt > c->L.orb.kp_cap) { set_error("descriptor count exceeds keypoint capacity"); return 1; }
+    return knn2_launch(q, nq, t, nt, nn, c->knn_scratch, (cudaStream_t)stream);
+}
+
+int ovo_match_points(ovo_ctx* c, const int32_t* nn, int nq, double thr, const float* kp1, const float* kp2, const float* disp1,
+                     const float* disp2, int32_t* matches, float* pts1, float* pts2, int32_t* counts, void* stream) {
+    CHECK_CTX(c, 1);
+    GatherParams p;
+    memcpy(p.Q, c->cfg.Q, sizeof(p.Q));
+    p.thr = thr; p.roi_x0 = c->L.x0; p.roi_y0 = c->L.y0; p.cw = c->L.cw; p.ch = c->L.ch; p.disp_pitch = c->L.cw;
+    return match_gather_launch(p, nn, nq, kp1, kp2, disp1, disp2, matches, pts1, pts2, counts, (cudaStream_t)stream);
+}
+
+int ovo_rigid_transform(ovo_ctx* c, const float* pts1, const float* pts2, const int32_t* count, int cap, double* out, void* stream) {
+    CHECK_CTX(c, 1);
+    return umeyama_launch(pts1, pts2, count, cap, out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

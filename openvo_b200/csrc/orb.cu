@@ -1,0 +1,543 @@
+// ORB (FAST-9/16 + NMS, Harris ranking, intensity-centroid orientation, rBRIEF-256 over an 8-level pyramid) for
+// sm_100a — stages 1+2 of the openVO hot path.
+//
+// Replaces cv2.ORB_create(nfeatures).detectAndCompute(img, mask) as called by the reference at
+// src/openVO/stereo_odometer.py:117 (object built at :22).  Semantics: SURVEY.md Appendix A.1-A.2 (bit-exact incl.
+// keypoint order; oracle = oracle/orb_restate.cpp).
+//
+// Phase 1 (device): pyramid (INTER_LINEAR_EXACT, chained) of image and mask -> FAST score plane -> NMS + mask + border
+//   test, emitted in raster order by a count / scan / emit triple -> Harris response of every candidate -> float32
+//   separable Gaussian with OpenCV's AVX2 FMA-body / scalar-tail split.
+// Host: the two KeyPointsFilter::retainBest passes (libstdc++ introselect permutation, host_select.cpp).
+// Phase 2 (device): one warp per kept keypoint: IC angle (integer moments, warp reduction) and the 256 rBRIEF tests.
+// All float arithmetic uses explicit __f*_rn intrinsics so that nvcc contracts nothing that OpenCV did not.
+#include "common.cuh"
+#include <cmath>
+
+namespace ovo {
+
+namespace {
+
+constexpr int kEdge = 31, kFastT = 20, kHalfPatch = 15;
+
+__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+__constant__ signed char c_pattern[1024] = {
+#include "orb_pattern.inc"
+};
+// 7-tap sigma=2 Gaussian, float32: k0..k3 (symmetric)
+__constant__ float c_gk[4] = {0x1.1f5f62p-4f, 0x1.0c70fcp-3f, 0x1.869472p-3f, 0x1.ba95c0p-3f};
+
+template <typename T>
+__device__ __forceinline__ T* fptr(T* p, size_t stride_bytes, int f) {
+    return (T*)((const uint8_t*)p + stride_bytes * (size_t)f);
+}
+
+// ---- pyramid ------------------------------------------------------------------------------------------------------
+// tab: per destination index (src index | c1 << 16), c1 = weight of src[index+1] in 1/256
+__global__ void k_orb_resize(OrbDims d, OrbWorkspace ws, size_t ws_stride, int level, const int32_t* __restrict__ xtab,
+                             const int32_t* __restrict__ ytab, int has_mask) {
+    const OrbLevel L = d.lv[level], S = d.lv[level - 1];
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
+    if (x >= L.w) return;
+    const int tx = xtab[x], ty = ytab[y];
+    const int i0 = tx & 0xFFFF, cx = tx >> 16, j0 = ty & 0xFFFF, cy = ty >> 16;
+    const int i1 = min(i0 + 1, S.w - 1), j1 = min(j0 + 1, S.h - 1);
+    for (int pl = 0; pl < 1 + has_mask; pl++) {
+        uint8_t* base = fptr(pl ? ws.maskpyr : ws.pyr, ws_stride, f);
+        const uint8_t* r0 = base + S.off + (size_t)j0 * S.w;
+        const uint8_t* r1 = base + S.off + (size_t)j1 * S.w;
+        const uint32_t h0 = r0[i0] * (256 - cx) + r0[i1] * cx;
+        const uint32_t h1 = r1[i0] * (256 - cx) + r1[i1] * cx;
+        uint32_t v = (h0 * (256 - cy) + h1 * cy + (1u << 15)) >> 16;
+        if (pl) v = v > 254 ? v : 0;  // THRESH_TOZERO(254) on the mask levels
+        base[L.off + (size_t)y * L.w + x] = (uint8_t)v;
+    }
+}
+
+__global__ void k_orb_copy_level0(OrbDims d, OrbWorkspace ws, size_t ws_stride, const uint8_t* __restrict__ img, int pitch,
+                                  size_t frame_stride, const uint8_t* __restrict__ mask, int mask_pitch, size_t mask_frame_stride) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
+    if (x >= d.W) return;
+    fptr(ws.pyr, ws_stride, f)[(size_t)y * d.W + x] = img[frame_stride * f + (size_t)y * pitch + x];
+    if (mask) fptr(ws.maskpyr, ws_stride, f)[(size_t)y * d.W + x] = mask[mask_frame_stride * f + (size_t)y * mask_pitch + x];
+}
+
+// ---- FAST-9/16 score ----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int arc9_max_of_min(const int (&v)[16]) {
+    // max over the 16 arcs of (min over 9 consecutive ring values)
+    int m2[16], m4[16], m8[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) m2[k] = min(v[k], v[(k + 1) & 15]);
+#pragma unroll
+    for (int k = 0; k < 16; k++) m4[k] = min(m2[k], m2[(k + 2) & 15]);
+#pragma unroll
+    for (int k = 0; k < 16; k++) m8[k] = min(m4[k], m4[(k + 4) & 15]);
+    int best = -1000;
+#pragma unroll
+    for (int k = 0; k < 16; k++) best = max(best, min(m8[k], v[(k + 8) & 15]));
+    return best;
+}
+
+constexpr int kFastTX = 32, kFastTY = 8;
+
+__global__ void __launch_bounds__(kFastTX* kFastTY) k_orb_fast(OrbDims d, OrbWorkspace ws, size_t ws_stride) {
+    __shared__ uint8_t tile[kFastTY + 6][kFastTX + 8];
+    const int level = blockIdx.z % ORB_NLEVELS, f = blockIdx.z / ORB_NLEVELS;
+    const OrbLevel L = d.lv[level];
+    const int x0 = blockIdx.x * kFastTX, y0 = blockIdx.y * kFastTY;
+    if (x0 >= L.w || y0 >= L.h) return;
+    const uint8_t* img = fptr(ws.pyr, ws_stride, f) + L.off;
+    const int tid = threadIdx.y * kFastTX + threadIdx.x;
+    for (int i = tid; i < (kFastTY + 6) * (kFastTX + 6); i += kFastTX * kFastTY) {
+        const int ty = i / (kFastTX + 6), tx = i % (kFastTX + 6);
+        const int gx = min(max(x0 + tx - 3, 0), L.w - 1), gy = min(max(y0 + ty - 3, 0), L.h - 1);
+        tile[ty][tx] = img[(size_t)gy * L.w + gx];
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x >= L.w || y >= L.h) return;
+    int score = 0;
+    if (x >= 3 && x < L.w - 3 && y >= 3 && y < L.h - 3) {
+        const int cx = threadIdx.x + 3, cy = threadIdx.y + 3;
+        const int c = tile[cy][cx];
+        int v[16];
+        v[0] = c - tile[cy + 3][cx];      v[1] = c - tile[cy + 3][cx + 1];  v[2] = c - tile[cy + 2][cx + 2];  v[3] = c - tile[cy + 1][cx + 3];
+        v[4] = c - tile[cy][cx + 3];      v[5] = c - tile[cy - 1][cx + 3];  v[6] = c - tile[cy - 2][cx + 2];  v[7] = c - tile[cy - 3][cx + 1];
+        v[8] = c - tile[cy - 3][cx];      v[9] = c - tile[cy - 3][cx - 1];  v[10] = c - tile[cy - 2][cx - 2]; v[11] = c - tile[cy - 1][cx - 3];
+        v[12] = c - tile[cy][cx - 3];     v[13] = c - tile[cy + 1][cx - 3]; v[14] = c - tile[cy + 2][cx - 2]; v[15] = c - tile[cy + 3][cx - 1];
+        uint32_t mb = 0, md = 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            mb |= (v[k] > kFastT ? 1u : 0u) << k;
+            md |= (v[k] < -kFastT ? 1u : 0u) << k;
+        }
+        auto has9 = [](uint32_t m) {
+            m |= m << 16;
+            uint32_t t = m & (m >> 1);
+            t &= t >> 2;
+            t &= t >> 4;
+            t &= m >> 8;
+            return (t & 0xFFFFu) != 0;
+        };
+        if (has9(mb) || has9(md)) {
+            int nv[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) nv[k] = -v[k];
+            const int m = max(arc9_max_of_min(v), arc9_max_of_min(nv));
+            score = m - 1;  // largest threshold for which the pixel is still a corner
+        }
+    }
+    fptr(ws.score, ws_stride, f)[L.off + (size_t)y * L.w + x] = (uint8_t)score;
+}
+
+// ---- NMS + mask + border, emitted in raster order --------------------------------------------------------------------------
+__device__ __forceinline__ bool is_candidate(const uint8_t* sc, const uint8_t* mk, int w, int x, int y) {
+    const uint8_t* p = sc + (size_t)y * w + x;
+    const int s = p[0];
+    if (s == 0) return false;
+    if (p[-1] >= s || p[1] >= s || p[-w - 1] >= s || p[-w] >= s || p[-w + 1] >= s || p[w - 1] >= s || p[w] >= s || p[w + 1] >= s)
+        return false;
+    return mk == nullptr || mk[(size_t)y * w + x] != 0;
+}
+
+template <bool EMIT>
+__global__ void __launch_bounds__(256) k_orb_nms(OrbDims d, OrbWorkspace ws, size_t ws_stride, int has_mask) {
+    const int level = blockIdx.y, f = blockIdx.z;
+    const OrbLevel L = d.lv[level];
+    const int lane = threadIdx.x & 31;
+    const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (y >= L.h) return;
+    int32_t* row_count = fptr(ws.row_count, ws_stride, f) + L.row_off;
+    const bool inside = y >= kEdge && y < L.h - kEdge;
+    const uint8_t* sc = fptr(ws.score, ws_stride, f) + L.off;
+    const uint8_t* mk = has_mask ? fptr(ws.maskpyr, ws_stride, f) + L.off : nullptr;
+    int base = 0;
+    int32_t* cxy = nullptr;
+    float* cresp = nullptr;
+    if (EMIT) {
+        const int32_t* lvl = fptr(ws.lvl_count, ws_stride, f);
+        base = lvl[ORB_NLEVELS + level] + fptr(ws.row_offset, ws_stride, f)[L.row_off + y];
+        cxy = fptr(ws.cand_xy, ws_stride, f);
+        cresp = fptr(ws.cand_resp, ws_stride, f);
+    }
+    int count = 0;
+    if (inside) {
+        for (int xb = kEdge; xb < L.w - kEdge; xb += 32) {
+            const int x = xb + lane;
+            const bool c = x < L.w - kEdge && is_candidate(sc, mk, L.w, x, y);
+            const uint32_t bal = __ballot_sync(0xffffffffu, c);
+            if (EMIT && c) {
+                const int idx = base + count + __popc(bal & ((1u << lane) - 1));
+                if (idx < d.cand_cap) {
+                    cxy[idx] = (y << 16) | x;
+                    cresp[2 * idx] = (float)sc[(size_t)y * L.w + x];
+                }
+            }
+            count += __popc(bal);
+        }
+    }
+    if (!EMIT && lane == 0) row_count[y] = count;
+}
+
+// one CTA per frame: exclusive scan of the row counts of each level; lvl_count[0..7] = per-level totals,
+// lvl_count[8..15] = level base offsets, lvl_count[16] = total
+__global__ void __launch_bounds__(1024) k_orb_scan(OrbDims d, OrbWorkspace ws, size_t ws_stride) {
+    __shared__ int warp_sums[32];
+    __shared__ int carry;
+    const int f = blockIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int32_t* rc = fptr(ws.row_count, ws_stride, f);
+    int32_t* ro = fptr(ws.row_offset, ws_stride, f);
+    int32_t* lvl = fptr(ws.lvl_count, ws_stride, f);
+    int lvl_base = 0;
+    for (int l = 0; l < ORB_NLEVELS; l++) {
+        const OrbLevel L = d.lv[l];
+        if (threadIdx.x == 0) carry = 0;
+        __syncthreads();
+        for (int r0 = 0; r0 < L.h; r0 += 1024) {
+            const int r = r0 + threadIdx.x;
+            const int v = r < L.h ? rc[L.row_off + r] : 0;
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) warp_sums[wid] = incl;
+            __syncthreads();
+            if (wid == 0) {
+                int s = warp_sums[lane];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, s, o);
+                    if (lane >= o) s += t;
+                }
+                warp_sums[lane] = s;
+            }
+            __syncthreads();
+            const int before = carry + (wid ? warp_sums[wid - 1] : 0) + incl - v;
+            if (r < L.h) ro[L.row_off + r] = before;
+            __syncthreads();
+            if (threadIdx.x == 1023) carry = before + v;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            lvl[l] = carry;
+            lvl[ORB_NLEVELS + l] = lvl_base;
+        }
+        lvl_base += carry;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) lvl[2 * ORB_NLEVELS] = lvl_base;
+}
+
+__device__ __forceinline__ int cand_level(const int32_t* lvl, int i) {
+    int l = 0;
+#pragma unroll
+    for (int k = 1; k < ORB_NLEVELS; k++) l += (i >= lvl[ORB_NLEVELS + k]) ? 1 : 0;
+    return l;
+}
+
+// ---- Harris response of every candidate (A.1.6) ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_orb_harris(OrbDims d, OrbWorkspace ws, size_t ws_stride) {
+    const int f = blockIdx.y;
+    const int32_t* lvl = fptr(ws.lvl_count, ws_stride, f);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= min(lvl[2 * ORB_NLEVELS], d.cand_cap)) return;
+    const OrbLevel L = d.lv[cand_level(lvl, i)];
+    const uint8_t* img = fptr(ws.pyr, ws_stride, f) + L.off;
+    const int xy = fptr(ws.cand_xy, ws_stride, f)[i];
+    const int x0 = xy & 0xFFFF, y0 = xy >> 16;
+    int a = 0, b = 0, c = 0;
+    for (int y = y0 - 3; y <= y0 + 3; y++) {
+        const uint8_t* rm = img + (size_t)(y - 1) * L.w + x0;
+        const uint8_t* r0 = rm + L.w;
+        const uint8_t* rp = r0 + L.w;
+#pragma unroll
+        for (int dx = -3; dx <= 3; dx++) {
+            const int Ix = 2 * ((int)r0[dx + 1] - (int)r0[dx - 1]) + ((int)rm[dx + 1] - (int)rm[dx - 1]) + ((int)rp[dx + 1] - (int)rp[dx - 1]);
+            const int Iy = 2 * ((int)rp[dx] - (int)rm[dx]) + ((int)rp[dx - 1] - (int)rm[dx - 1]) + ((int)rp[dx + 1] - (int)rm[dx + 1]);
+            a += Ix * Ix;
+            b += Iy * Iy;
+            c += Ix * Iy;
+        }
+    }
+    const float scale = __fdiv_rn(1.f, 4.f * 7.f * 255.f);
+    const float s4 = __fmul_rn(__fmul_rn(__fmul_rn(scale, scale), scale), scale);
+    const float fa = (float)a, fb = (float)b, fc = (float)c;
+    const float det = __fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc));
+    const float tr = __fadd_rn(fa, fb);
+    const float resp = __fmul_rn(__fsub_rn(det, __fmul_rn(__fmul_rn(0.04f, tr), tr)), s4);
+    fptr(ws.cand_resp, ws_stride, f)[2 * i + 1] = resp;
+}
+
+// ---- float32 separable Gaussian with the AVX2 engine's body / tail split (A.2.1) -------------------------------------------
+constexpr int kBlurTX = 64, kBlurTY = 16;
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = i < 0 ? -i : 2 * (n - 1) - i;
+    return i;
+}
+
+__global__ void __launch_bounds__(256) k_orb_blur(OrbDims d, OrbWorkspace ws, size_t ws_stride) {
+    __shared__ uint8_t src[kBlurTY + 6][kBlurTX + 8];
+    __shared__ float rows[kBlurTY + 6][kBlurTX];
+    const int level = blockIdx.z % ORB_NLEVELS, f = blockIdx.z / ORB_NLEVELS;
+    const OrbLevel L = d.lv[level];
+    const int x0 = blockIdx.x * kBlurTX, y0 = blockIdx.y * kBlurTY;
+    if (x0 >= L.w || y0 >= L.h) return;
+    const uint8_t* img = fptr(ws.pyr, ws_stride, f) + L.off;
+    for (int i = threadIdx.x; i < (kBlurTY + 6) * (kBlurTX + 6); i += 256) {
+        const int ty = i / (kBlurTX + 6), tx = i % (kBlurTX + 6);
+        src[ty][tx] = img[(size_t)reflect101(y0 + ty - 3, L.h) * L.w + reflect101(x0 + tx - 3, L.w)];
+    }
+    __syncthreads();
+    const float k0 = c_gk[0], k1 = c_gk[1], k2 = c_gk[2], k3 = c_gk[3];
+    const int wbody = (L.w / 32) * 32, wcol = (L.w / 4) * 4;
+    for (int i = threadIdx.x; i < (kBlurTY + 6) * kBlurTX; i += 256) {
+        const int ty = i / kBlurTX, tx = i % kBlurTX;
+        const float p0 = src[ty][tx], p1 = src[ty][tx + 1], p2 = src[ty][tx + 2], p3 = src[ty][tx + 3], p4 = src[ty][tx + 4],
+                    p5 = src[ty][tx + 5], p6 = src[ty][tx + 6];
+        float acc;
+        if (x0 + tx < wbody) {
+            acc = __fmaf_rn(k0, p0, 0.f);
+            acc = __fmaf_rn(k1, p1, acc); acc = __fmaf_rn(k2, p2, acc); acc = __fmaf_rn(k3, p3, acc);
+            acc = __fmaf_rn(k2, p4, acc); acc = __fmaf_rn(k1, p5, acc); acc = __fmaf_rn(k0, p6, acc);
+        } else {
+            acc = __fmul_rn(k0, p0);
+            acc = __fadd_rn(acc, __fmul_rn(k1, p1)); acc = __fadd_rn(acc, __fmul_rn(k2, p2)); acc = __fadd_rn(acc, __fmul_rn(k3, p3));
+            acc = __fadd_rn(acc, __fmul_rn(k2, p4)); acc = __fadd_rn(acc, __fmul_rn(k1, p5)); acc = __fadd_rn(acc, __fmul_rn(k0, p6));
+        }
+        rows[ty][tx] = acc;
+    }
+    __syncthreads();
+    uint8_t* out = fptr(ws.blur, ws_stride, f) + L.off;
+    for (int i = threadIdx.x; i < kBlurTY * kBlurTX; i += 256) {
+        const int ty = i / kBlurTX, tx = i % kBlurTX;
+        const int x = x0 + tx, y = y0 + ty;
+        if (x >= L.w || y >= L.h) continue;
+        float c = __fmul_rn(k3, rows[ty + 3][tx]);
+        const float s1 = __fadd_rn(rows[ty + 4][tx], rows[ty + 2][tx]);
+        const float s2 = __fadd_rn(rows[ty + 5][tx], rows[ty + 1][tx]);
+        const float s3 = __fadd_rn(rows[ty + 6][tx], rows[ty][tx]);
+        if (x < wcol) {
+            c = __fmaf_rn(k2, s1, c); c = __fmaf_rn(k1, s2, c); c = __fmaf_rn(k0, s3, c);
+        } else {
+            c = __fadd_rn(c, __fmul_rn(k2, s1)); c = __fadd_rn(c, __fmul_rn(k1, s2)); c = __fadd_rn(c, __fmul_rn(k0, s3));
+        }
+        const int v = __float2int_rn(c);
+        out[(size_t)y * L.w + x] = (uint8_t)min(max(v, 0), 255);
+    }
+}
+
+// ---- phase 2: orientation + descriptor, one warp per kept keypoint -----------------------------------------------------------
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+    const float s = (float)(180.0 / 3.14159265358979323846);
+    const float p1 = __fmul_rn(0.9997878412794807f, s), p3 = __fmul_rn(-0.3258083974640975f, s);
+    const float p5 = __fmul_rn(0.1555786518463281f, s), p7 = __fmul_rn(-0.04432655554792128f, s);
+    const float eps = (float)2.2204460492503131e-16;
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a;
+    if (ax >= ay) {
+        const float c = __fdiv_rn(ay, __fadd_rn(ax, eps)), c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        const float c = __fdiv_rn(ax, __fadd_rn(ay, eps)), c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+__global__ void __launch_bounds__(128) k_orb_describe(OrbDims d, OrbWorkspace ws, size_t ws_stride, const int32_t* __restrict__ n_sel,
+                                                      float* __restrict__ kp_out, uint8_t* __restrict__ desc_out) {
+    const int f = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (k >= n_sel[f]) return;
+    const int32_t* lvl = fptr(ws.lvl_count, ws_stride, f);
+    const int ci = fptr(ws.sel, ws_stride, f)[k];
+    const int level = cand_level(lvl, ci);
+    const OrbLevel L = d.lv[level];
+    const int xy = fptr(ws.cand_xy, ws_stride, f)[ci];
+    const int x0 = xy & 0xFFFF, y0 = xy >> 16;
+    const uint8_t* img = fptr(ws.pyr, ws_stride, f) + L.off;
+    // IC angle (A.1.7): lane v+15 sums row v
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+        const int v = lane - kHalfPatch;
+        const int um = c_umax[abs(v)];
+        const uint8_t* r = img + (size_t)(y0 + v) * L.w + x0;
+        int rs = 0;
+        for (int u = -um; u <= um; u++) {
+            const int p = r[u];
+            m10 += u * p;
+            rs += p;
+        }
+        m01 = v * rs;
+    }
+    m10 = __reduce_add_sync(0xffffffffu, m10);
+    m01 = __reduce_add_sync(0xffffffffu, m01);
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+    const float ptx = __fmul_rn((float)x0, L.scale), pty = __fmul_rn((float)y0, L.scale);
+    if (lane == 0) {
+        float* o = kp_out + ((size_t)f * d.kp_cap + k) * 6;
+        o[0] = ptx; o[1] = pty; o[2] = __fmul_rn(31.f, L.scale); o[3] = angle;
+        o[4] = fptr(ws.cand_resp, ws_stride, f)[2 * ci + 1];
+        o[5] = (float)level;
+    }
+    // rBRIEF (A.2.2): lane i produces descriptor byte i
+    const float ang = __fmul_rn(angle, (float)(3.14159265358979323846 / 180.f));
+    const float ca = (float)cos((double)ang), sa = (float)sin((double)ang);
+    const int cx = __float2int_rn(__fmul_rn(ptx, L.inv)), cy = __float2int_rn(__fmul_rn(pty, L.inv));
+    const uint8_t* bl = fptr(ws.blur, ws_stride, f) + L.off;
+    uint32_t byte = 0;
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+        const signed char* q = c_pattern + (lane * 8 + b) * 4;
+        int val[2];
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const float px = (float)q[2 * e], py = (float)q[2 * e + 1];
+            const float rx = __fsub_rn(__fmul_rn(px, ca), __fmul_rn(py, sa));
+            const float ry = __fadd_rn(__fmul_rn(px, sa), __fmul_rn(py, ca));
+            val[e] = bl[(size_t)(cy + __float2int_rn(ry)) * L.w + (cx + __float2int_rn(rx))];
+        }
+        byte |= (val[0] < val[1] ? 1u : 0u) << b;
+    }
+    desc_out[((size_t)f * d.kp_cap + k) * 32 + lane] = (uint8_t)byte;
+}
+
+}  // namespace
+
+// ---- host side ---------------------------------------------------------------------------------------------------------
+void orb_make_dims(int W, int H, int nfeatures, OrbDims* d) {
+    // SURVEY.md A.1.1 — float32 arithmetic exactly as OpenCV's ORB_Impl does it
+    d->W = W; d->H = H; d->nfeatures = nfeatures;
+    const float scaleFactor = 1.2f;
+    int off = 0, rows = 0;
+    for (int l = 0; l < ORB_NLEVELS; l++) {
+        OrbLevel& L = d->lv[l];
+        L.scale = (float)std::pow((double)scaleFactor, (double)l);
+        L.inv = 1.0f / L.scale;
+        L.w = (int)lrintf((float)W * L.inv);
+        L.h = (int)lrintf((float)H * L.inv);
+        L.off = off; L.row_off = rows;
+        off += (L.w * L.h + 15) / 16 * 16;
+        rows += L.h;
+    }
+    d->total_px = off; d->total_rows = rows;
+    float factor = (float)(1.0 / (double)scaleFactor);
+    float nd = nfeatures * (1 - factor) / (1 - (float)std::pow((double)factor, (double)ORB_NLEVELS));
+    int sum = 0;
+    for (int l = 0; l < ORB_NLEVELS - 1; l++) {
+        d->lv[l].nfeat = (int)lrintf(nd);
+        sum += d->lv[l].nfeat;
+        nd *= factor;
+    }
+    d->lv[ORB_NLEVELS - 1].nfeat = nfeatures - sum > 0 ? nfeatures - sum : 0;
+    d->cand_cap = off / 4 + 1024;  // strict 3x3 NMS leaves at most one candidate per 2x2 block
+    d->kp_cap = nfeatures + nfeatures / 8 + 64;
+}
+
+size_t orb_workspace_bytes(const OrbDims& d) {
+    size_t b = 0;
+    b += 4 * align_up((size_t)d.total_px + 64, 256);
+    b += 2 * align_up((size_t)d.total_rows * 4, 256);
+    b += align_up(32 * 4, 256);
+    b += align_up((size_t)d.cand_cap * 4, 256) + align_up((size_t)d.cand_cap * 8, 256);
+    b += align_up((size_t)d.kp_cap * 4, 256);
+    return b;
+}
+
+void orb_carve(const OrbDims& d, uint8_t* base, OrbWorkspace* ws) {
+    uint8_t* p = base;
+    const size_t px = align_up((size_t)d.total_px + 64, 256);
+    ws->pyr = p; p += px;
+    ws->maskpyr = p; p += px;
+    ws->score = p; p += px;
+    ws->blur = p; p += px;
+    ws->row_count = (int32_t*)p; p += align_up((size_t)d.total_rows * 4, 256);
+    ws->row_offset = (int32_t*)p; p += align_up((size_t)d.total_rows * 4, 256);
+    ws->lvl_count = (int32_t*)p; p += align_up(32 * 4, 256);
+    ws->cand_xy = (int32_t*)p; p += align_up((size_t)d.cand_cap * 4, 256);
+    ws->cand_resp = (float*)p; p += align_up((size_t)d.cand_cap * 8, 256);
+    ws->sel = (int32_t*)p; p += align_up((size_t)d.kp_cap * 4, 256);
+}
+
+// resize tables (host): for level l >= 1, xtab at tab + tab_off[l][0] (w_l entries), ytab at tab + tab_off[l][1]
+void orb_make_resize_tables(const OrbDims& d, int32_t* tab, int* tab_off /*[8][2]*/, int* total) {
+    int off = 0;
+    for (int l = 1; l < ORB_NLEVELS; l++) {
+        for (int ax = 0; ax < 2; ax++) {
+            const int s = ax == 0 ? d.lv[l - 1].w : d.lv[l - 1].h, t = ax == 0 ? d.lv[l].w : d.lv[l].h;
+            tab_off[2 * l + ax] = off;
+            const double scale = 1.0 / ((double)t / (double)s);
+            for (int v = 0; v < t; v++) {
+                const double fv = scale * (v + 0.5) - 0.5;
+                int i = (int)std::floor(fv);
+                int c = (int)std::nearbyint((fv - i) * 256.0);
+                if (i < 0) { i = 0; c = 0; }
+                if (i >= s - 1) { i = s - 1; c = 0; }
+                if (tab) tab[off + v] = i | (c << 16);
+            }
+            off += t;
+        }
+    }
+    *total = off;
+}
+
+int orb_phase1_launch(const OrbDims& d, const OrbWorkspace* ws0, size_t ws_stride, const int32_t* tab_dev, const int* tab_off, int nb,
+                      const uint8_t* img, int pitch, size_t frame_stride, const uint8_t* mask, int mask_pitch,
+                      size_t mask_frame_stride, cudaStream_t st) {
+    const OrbWorkspace& ws = *ws0;
+    const int has_mask = mask != nullptr;
+    {
+        dim3 grid(cdiv(d.W, 128), d.H, nb);
+        OVO_LAUNCH(k_orb_copy_level0, grid, dim3(128), 0, st, d, ws, ws_stride, img, pitch, frame_stride, mask, mask_pitch, mask_frame_stride);
+        OVO_LAUNCH_CHECK();
+    }
+    for (int l = 1; l < ORB_NLEVELS; l++) {
+        dim3 grid(cdiv(d.lv[l].w, 128), d.lv[l].h, nb);
+        OVO_LAUNCH(k_orb_resize, grid, dim3(128), 0, st, d, ws, ws_stride, l, tab_dev + tab_off[2 * l], tab_dev + tab_off[2 * l + 1], has_mask);
+        OVO_LAUNCH_CHECK();
+    }
+    {
+        dim3 grid(cdiv(d.W, kFastTX), cdiv(d.H, kFastTY), nb * ORB_NLEVELS);
+        OVO_LAUNCH(k_orb_fast, grid, dim3(kFastTX, kFastTY), 0, st, d, ws, ws_stride);
+        OVO_LAUNCH_CHECK();
+    }
+    {
+        dim3 grid(cdiv(d.H, 8), ORB_NLEVELS, nb);
+        OVO_LAUNCH(k_orb_nms<false>, grid, dim3(256), 0, st, d, ws, ws_stride, has_mask);
+        OVO_LAUNCH_CHECK();
+        OVO_LAUNCH(k_orb_scan, dim3(nb), dim3(1024), 0, st, d, ws, ws_stride);
+        OVO_LAUNCH_CHECK();
+        OVO_LAUNCH(k_orb_nms<true>, grid, dim3(256), 0, st, d, ws, ws_stride, has_mask);
+        OVO_LAUNCH_CHECK();
+    }
+    {
+        dim3 grid(cdiv(d.cand_cap, 128), nb);
+        OVO_LAUNCH(k_orb_harris, grid, dim3(128), 0, st, d, ws, ws_stride);
+        OVO_LAUNCH_CHECK();
+    }
+    {
+        dim3 grid(cdiv(d.W, kBlurTX), cdiv(d.H, kBlurTY), nb * ORB_NLEVELS);
+        OVO_LAUNCH(k_orb_blur, grid, dim3(256), 0, st, d, ws, ws_stride);
+        OVO_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+int orb_phase2_launch(const OrbDims& d, const OrbWorkspace* ws0, size_t ws_stride, int nb, int max_sel, const int32_t* n_sel_dev,
+                      float* kp_out, uint8_t* desc_out, cudaStream_t st) {
+    if (max_sel <= 0) return 0;
+    dim3 grid(cdiv(max_sel, 4), nb);
+    OVO_LAUNCH(k_orb_describe, grid, dim3(128), 0, st, d, *ws0, ws_stride, n_sel_dev, kp_out, desc_out);
+    OVO_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace ovo

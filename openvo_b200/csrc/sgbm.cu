@@ -1,0 +1,627 @@
+// StereoSGBM (MODE_SGBM, 5 directions) for sm_100a — stage 4 of the openVO hot path.
+//
+// Replaces cv2.StereoSGBM.compute as called by the reference at src/openVO/stereo_camera.py:51 (object built at
+// :23-27).  Semantics: SURVEY.md Appendix A.4 (bit-exact; oracle = oracle/sgbm_restate.cpp).
+//
+// Data flow (per frame, all in HBM/L2; D padded to Dp in {64,128,256} so that one warp owns one cost vector):
+//   k_sgbm_prep   images -> byte-packed (v, vmin, vmax) planes for the Sobel-x-clipped and the raw rows (A.4.1)
+//   k_sgbm_cost   prep   -> C[y][x1][d] int16 : Birchfield-Tomasi cost summed over the blockSize^2 window (A.4.2)
+//   k_sgbm_vert   C      -> Lv[3][y][x1][d]   : paths from (x-1,y-1), (x,y-1), (x+1,y-1); one warp per scan line
+//   k_sgbm_horiz  C, Lv  -> raw disparity     : paths from (x-1,y) and (x+1,y) run towards each other by two warps
+//                                               per row; whoever reaches a cell second owns the complete 5-path sum
+//                                               and does WTA / uniqueness / sub-pixel / disp2; then the LR check
+//   k_median3, k_ccl_*   -> 3x3 median and speckle filter (connected components, union-find)
+// All cost arithmetic is packed 2 x u16 per register on the DPX pipe (VIADDMNMX.U16x2 / VIMNMX.U16x2); the per-cell
+// minimum is one CREDUX.MIN.  No tensor cores: nothing here is a contraction.
+#include "common.cuh"
+
+namespace ovo {
+
+namespace {
+
+constexpr uint32_t kMaxC2 = 0x7FFF7FFFu;  // MAX_COST in both halves
+constexpr int kInv = -16;                 // (minDisparity - 1) * 16
+constexpr uint32_t kD2Init = 0xFFFFFFFFu;
+
+__device__ __forceinline__ uint32_t bcast16(uint32_t v) { return v * 0x10001u; }
+
+template <typename T>
+__device__ __forceinline__ T* frame_ptr(T* p, size_t stride_bytes, int f) {
+    return (T*)((const uint8_t*)p + stride_bytes * (size_t)f);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// A.4.1 row preparation.  One word per pixel and row type: byte0 = v, byte1 = min(vl, vr, v), byte2 = max(...).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_sgbm_prep(const uint8_t* __restrict__ left, const uint8_t* __restrict__ right, int pitch,
+                            size_t frame_stride, SgbmDims d, SgbmWorkspace ws, size_t ws_stride) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int f = blockIdx.z >> 1, im = blockIdx.z & 1;
+    if (x >= d.W) return;
+    const int W = d.W, H = d.H, ftzero = d.ftzero;
+    const uint8_t* I = (im ? right : left) + frame_stride * (size_t)f;
+    const uint8_t* r = I + (size_t)y * pitch;
+    const uint8_t* rn = I + (size_t)max(y - 1, 0) * pitch;
+    const uint8_t* rs = I + (size_t)min(y + 1, H - 1) * pitch;
+    uint32_t* out = frame_ptr(ws.prep, ws_stride, f) + (size_t)im * 2 * H * W;
+    auto G = [&](int xx) -> int {
+        if (xx <= 0 || xx >= W - 1) return ftzero;
+        int v = 2 * ((int)r[xx + 1] - (int)r[xx - 1]) + ((int)rn[xx + 1] - (int)rn[xx - 1]) + ((int)rs[xx + 1] - (int)rs[xx - 1]);
+        return min(max(v, -ftzero), ftzero) + ftzero;
+    };
+    auto R = [&](int xx) -> int { return (xx <= 0 || xx >= W - 1) ? ftzero : (int)r[xx]; };
+    {
+        int c = G(x), vl = x > 0 ? (c + G(x - 1)) >> 1 : c, vr = x < W - 1 ? (c + G(x + 1)) >> 1 : c;
+        out[(size_t)y * W + x] = (uint32_t)c | ((uint32_t)min(min(vl, vr), c) << 8) | ((uint32_t)max(max(vl, vr), c) << 16);
+    }
+    {
+        int c = R(x), vl = x > 0 ? (c + R(x - 1)) >> 1 : c, vr = x < W - 1 ? (c + R(x + 1)) >> 1 : c;
+        out[(size_t)H * W + (size_t)y * W + x] = (uint32_t)c | ((uint32_t)min(min(vl, vr), c) << 8) | ((uint32_t)max(max(vl, vr), c) << 16);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// A.4.1 + A.4.2 cost volume.  A thread owns one disparity pair (d, d+1) of one unit = (TX columns) x (RS rows); it
+// walks the rows of the strip, and inside a row the TX + 2*SW2 columns, keeping the horizontal window in registers
+// and the vertical window as a ring of horizontal sums in (thread-private, conflict-free) shared memory.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kCostThreads = 128;
+constexpr int kCostRS = 32;
+
+__device__ __forceinline__ uint32_t bt_pair(uint32_t lw, uint32_t rw0, uint32_t rw1) {
+    // lw: left word at x; rw0 / rw1: right words at x-d and x-d-1
+    const uint32_t v = __byte_perm(rw0, rw1, 0x7430), vmin = __byte_perm(rw0, rw1, 0x7531), vmax = __byte_perm(rw0, rw1, 0x7632);
+    const uint32_t u = __byte_perm(lw, 0, 0x4040), umin = __byte_perm(lw, 0, 0x4141), umax = __byte_perm(lw, 0, 0x4242);
+    const uint32_t c0 = __vmaxu2(vmin, u) - __vminu2(vmax, u);  // max(0, u - vmax, vmin - u), both halves
+    const uint32_t c1 = __vmaxu2(umin, v) - __vminu2(umax, v);  // max(0, v - umax, umin - v)
+    return __vminu2(c0, c1);
+}
+
+template <int SW2, int TX>
+__global__ void __launch_bounds__(kCostThreads) k_sgbm_cost(SgbmDims d, SgbmWorkspace ws, size_t ws_stride) {
+    constexpr int BS = 2 * SW2 + 1;
+    __shared__ uint32_t ring[BS * TX * kCostThreads];
+    const int npairs = d.Dp >> 1;
+    const int tid = threadIdx.y * npairs + threadIdx.x;
+    const int n_xt = (d.W1 + TX - 1) / TX, n_ys = (d.H + kCostRS - 1) / kCostRS;
+    const int unit = blockIdx.x * blockDim.y + threadIdx.y;
+    if (unit >= n_xt * n_ys) return;
+    const int x0 = (unit % n_xt) * TX, y0 = (unit / n_xt) * kCostRS;
+    const int f = blockIdx.z;
+    const int W = d.W, H = d.H, D = d.D, W1 = d.W1;
+    const int d0 = 2 * threadIdx.x;
+    const bool pad = d0 >= D;
+    const uint32_t* prep = frame_ptr(ws.prep, ws_stride, f);
+    const size_t plane = (size_t)H * W;
+    uint32_t* Cw = reinterpret_cast<uint32_t*>(frame_ptr(ws.C, ws_stride, f));
+    const int yend = min(y0 + kCostRS, H);
+
+    uint32_t vs[TX];
+#pragma unroll
+    for (int c = 0; c < TX; c++) vs[c] = 0;
+
+    int k = 0;  // rows accumulated so far
+    for (int r = y0 - SW2; r < yend + SW2; r++, k++) {
+        const int yc = min(max(r, 0), H - 1);
+        const uint32_t* Lg = prep + (size_t)yc * W;
+        const uint32_t* Lr = Lg + plane;
+        const uint32_t* Rg = Lg + 2 * plane;
+        const uint32_t* Rr = Lg + 3 * plane;
+        uint32_t* slot = ring + (size_t)(k % BS) * TX * kCostThreads + tid;
+        uint32_t win[BS];
+#pragma unroll
+        for (int i = 0; i < BS; i++) win[i] = 0;
+        uint32_t hs = 0;
+#pragma unroll
+        for (int j = -SW2; j < TX + SW2; j++) {
+            uint32_t pix = 0;
+            if (!pad) {
+                const int xx = min(max(x0 + j, 0), W1 - 1);
+                const int x = xx + D, xr = x - d0;
+                const uint32_t cg = bt_pair(__ldg(Lg + x), __ldg(Rg + xr), __ldg(Rg + xr - 1));
+                const uint32_t cr = bt_pair(__ldg(Lr + x), __ldg(Rr + xr), __ldg(Rr + xr - 1));
+                pix = cg + ((cr >> 2) & 0x3FFF3FFFu);
+            }
+            hs = hs + pix - win[0];
+#pragma unroll
+            for (int i = 0; i < BS - 1; i++) win[i] = win[i + 1];
+            win[BS - 1] = pix;
+            if (j >= SW2) {
+                const int c = j - SW2;
+                const uint32_t old = k >= BS ? slot[c * kCostThreads] : 0u;
+                vs[c] = vs[c] - old + hs;
+                slot[c * kCostThreads] = hs;
+            }
+        }
+        const int y = r - SW2;
+        if (y >= y0) {
+            uint32_t* out = Cw + ((size_t)y * W1 + x0) * npairs + threadIdx.x;
+#pragma unroll
+            for (int c = 0; c < TX; c++)
+                if (x0 + c < W1) out[(size_t)c * npairs] = vs[c];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// A.4.3 one path step on a warp-wide cost vector.  Lane l owns d in [2*NPR*l, 2*NPR*(l+1)), two per register.
+// ------------------------------------------------------------------------------------------------------------
+template <int NPR>
+struct PathState {
+    uint32_t L[NPR];
+    uint32_t m;  // min over d of L (warp-uniform)
+};
+
+template <int NPR>
+__device__ __forceinline__ void path_reset(PathState<NPR>& s) {
+#pragma unroll
+    for (int r = 0; r < NPR; r++) s.L[r] = 0;
+    s.m = 0;
+}
+
+template <int NPR>
+__device__ __forceinline__ void path_step(PathState<NPR>& s, const uint32_t (&c)[NPR], const uint32_t (&padmask)[NPR],
+                                          uint32_t P1P1, uint32_t P2, int lane) {
+    uint32_t below = __shfl_up_sync(0xffffffffu, s.L[NPR - 1], 1);  // neighbour lane's top pair
+    uint32_t above = __shfl_down_sync(0xffffffffu, s.L[0], 1);      // neighbour lane's bottom pair
+    if (lane == 0) below = kMaxC2;                                   // Lp[-1] = MAX_COST
+    if (lane == 31) above = kMaxC2;                                  // Lp[D]  = MAX_COST
+    const uint32_t mP2 = bcast16(s.m + P2), mm = bcast16(s.m);
+    uint32_t out[NPR];
+#pragma unroll
+    for (int r = 0; r < NPR; r++) {
+        const uint32_t dm1 = __funnelshift_l(r == 0 ? below : s.L[r - 1], s.L[r], 16);       // Lp[d-1]
+        const uint32_t dp1 = __funnelshift_r(s.L[r], r == NPR - 1 ? above : s.L[r + 1], 16); // Lp[d+1]
+        uint32_t t = __viaddmin_u16x2(dm1, P1P1, s.L[r]);
+        t = __viaddmin_u16x2(dp1, P1P1, t);
+        t = __vminu2(t, mP2);
+        out[r] = (c[r] + (t - mm)) | padmask[r];
+    }
+    uint32_t t = out[0];
+#pragma unroll
+    for (int r = 0; r < NPR; r++) {
+        s.L[r] = out[r];
+        if (r) t = __vminu2(t, out[r]);
+    }
+    s.m = __reduce_min_sync(0xffffffffu, min(t & 0xFFFFu, t >> 16));
+}
+
+template <int NPR>
+__device__ __forceinline__ void path_start(PathState<NPR>& s, const uint32_t (&c)[NPR], const uint32_t (&padmask)[NPR]) {
+    // predecessor outside the image: L = C
+    uint32_t t = kMaxC2;
+#pragma unroll
+    for (int r = 0; r < NPR; r++) {
+        s.L[r] = c[r] | padmask[r];
+        t = __vminu2(t, s.L[r]);
+    }
+    s.m = __reduce_min_sync(0xffffffffu, min(t & 0xFFFFu, t >> 16));
+}
+
+template <int NPR>
+__device__ __forceinline__ void make_padmask(uint32_t (&padmask)[NPR], int lane, int D) {
+#pragma unroll
+    for (int r = 0; r < NPR; r++) padmask[r] = (2 * (NPR * lane + r) >= D) ? kMaxC2 : 0u;
+}
+
+template <int NPR>
+__device__ __forceinline__ void ldv(uint32_t (&v)[NPR], const uint32_t* p) {
+    if constexpr (NPR == 4) {
+        const uint4 t = *reinterpret_cast<const uint4*>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else if constexpr (NPR == 2) {
+        const uint2 t = *reinterpret_cast<const uint2*>(p);
+        v[0] = t.x; v[1] = t.y;
+    } else {
+        v[0] = *p;
+    }
+}
+template <int NPR>
+__device__ __forceinline__ void stv(uint32_t* p, const uint32_t (&v)[NPR]) {
+    if constexpr (NPR == 4) *reinterpret_cast<uint4*>(p) = make_uint4(v[0], v[1], v[2], v[3]);
+    else if constexpr (NPR == 2) *reinterpret_cast<uint2*>(p) = make_uint2(v[0], v[1]);
+    else *p = v[0];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Paths 1..3 (top -> bottom).  One warp per scan line; a diagonal line that leaves the image on one side re-enters
+// on the other with a fresh (zero) predecessor, so every warp does exactly H steps.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kVertPF = 8;
+
+template <int NPR>
+__global__ void __launch_bounds__(256) k_sgbm_vert(SgbmDims d, SgbmWorkspace ws, size_t ws_stride) {
+    const int lane = threadIdx.x & 31;
+    const int line = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int dir = blockIdx.y, f = blockIdx.z;
+    const int W1 = d.W1, H = d.H;
+    if (line >= W1) return;
+    constexpr int WPC = 32 * NPR;  // words per cell
+    const uint32_t* C = reinterpret_cast<const uint32_t*>(frame_ptr(ws.C, ws_stride, f)) + lane * NPR;
+    uint32_t* Lout = reinterpret_cast<uint32_t*>(frame_ptr(ws.Lv, ws_stride, f)) + (size_t)dir * H * W1 * WPC + lane * NPR;
+    const int step = dir == 0 ? 1 : (dir == 2 ? -1 : 0);
+    auto advance = [&](int x) { x += step; return x >= W1 ? 0 : (x < 0 ? W1 - 1 : x); };
+    const int xreset = dir == 0 ? 0 : (dir == 2 ? W1 - 1 : -1);
+
+    uint32_t padmask[NPR];
+    make_padmask<NPR>(padmask, lane, d.D);
+    const uint32_t P1P1 = bcast16(d.P1), P2 = d.P2;
+
+    uint32_t cbuf[kVertPF][NPR];
+    int xpf = line;
+#pragma unroll
+    for (int i = 0; i < kVertPF; i++) {
+        if (i < H) ldv<NPR>(cbuf[i], C + ((size_t)i * W1 + xpf) * WPC);
+        xpf = advance(xpf);
+    }
+    PathState<NPR> s;
+    path_reset<NPR>(s);
+    int x = line;
+    for (int y0 = 0; y0 < H; y0 += kVertPF) {
+#pragma unroll
+        for (int i = 0; i < kVertPF; i++) {
+            const int y = y0 + i;
+            if (y < H) {
+                uint32_t c[NPR];
+#pragma unroll
+                for (int r = 0; r < NPR; r++) c[r] = cbuf[i][r];
+                if (y + kVertPF < H) ldv<NPR>(cbuf[i], C + ((size_t)(y + kVertPF) * W1 + xpf) * WPC);
+                xpf = advance(xpf);
+                if (y == 0 || x == xreset) path_start<NPR>(s, c, padmask);
+                else path_step<NPR>(s, c, padmask, P1P1, P2, lane);
+                stv<NPR>(Lout + ((size_t)y * W1 + x) * WPC, s.L);
+                x = advance(x);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Paths 0 and 4 + selection (A.4.4) + LR check (A.4.5).  One CTA (two warps) per row.  Warp 0 runs left -> right,
+// warp 1 right -> left.  In its first half a warp stores T = sat(L1+L2+L3+own) over Lv[1]; after the rendezvous each
+// warp reads the other's T, adds its own path and owns the complete S for the cell.  disp2 is order-independent:
+// min cost, ties to the larger x (= larger d), which is what the reference's right-to-left sweep keeps.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kHorPF = 4;
+
+template <int NPR>
+__device__ __forceinline__ void wta_cell(const uint32_t (&S)[NPR], int lane, const SgbmDims& d, int x1, int16_t* disp1s,
+                                         uint32_t* d2key) {
+    const int D = d.D;
+    uint32_t kbest = 0xFFFFFFFFu;
+#pragma unroll
+    for (int r = 0; r < NPR; r++) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const uint32_t v = (S[r] >> (16 * h)) & 0xFFFFu;
+            const int dd = 2 * (NPR * lane + r) + h;
+            if (dd < D) kbest = min(kbest, (v << 9) | (uint32_t)dd);
+        }
+    }
+    const uint32_t kmin = __reduce_min_sync(0xffffffffu, kbest);
+    const int minS = (int)(kmin >> 9), best = (int)(kmin & 511u);
+    bool bad = false;
+    uint32_t sm1 = 0, sp1 = 0;
+    const int lim = minS * 100, fac = 100 - d.uniq;
+#pragma unroll
+    for (int r = 0; r < NPR; r++) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int v = (int)((S[r] >> (16 * h)) & 0xFFFFu);
+            const int dd = 2 * (NPR * lane + r) + h;
+            if (dd < D) {
+                if (v * fac < lim && abs(dd - best) > 1) bad = true;
+                if (dd == best - 1) sm1 = (uint32_t)v;
+                if (dd == best + 1) sp1 = (uint32_t)v;
+            }
+        }
+    }
+    if (__any_sync(0xffffffffu, bad)) return;  // disp1 stays INVALID
+    sm1 = __reduce_max_sync(0xffffffffu, sm1);
+    sp1 = __reduce_max_sync(0xffffffffu, sp1);
+    if (lane == 0) {
+        const int x = x1 + D;
+        if (minS < 32767) atomicMin(&d2key[x - best], ((uint32_t)minS << 16) | (uint32_t)(0xFFFF - best));
+        int dsp = best * 16;
+        if (best > 0 && best < D - 1) {
+            const int den = max((int)sm1 + (int)sp1 - 2 * minS, 1);
+            dsp += (((int)sm1 - (int)sp1) * 16 + den) / (2 * den);
+        }
+        disp1s[x] = (int16_t)dsp;
+    }
+}
+
+template <int NPR>
+__global__ void __launch_bounds__(64) k_sgbm_horiz(SgbmDims d, SgbmWorkspace ws, size_t ws_stride) {
+    OVO_DYN_SMEM(uint32_t, hsm);
+    uint32_t* d2key = hsm;                                        // [W]
+    int16_t* disp1s = reinterpret_cast<int16_t*>(hsm + d.W);      // [W]
+    const int y = blockIdx.x, f = blockIdx.y;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int W = d.W, W1 = d.W1, H = d.H;
+    constexpr int WPC = 32 * NPR;
+    for (int i = threadIdx.x; i < W; i += blockDim.x) {
+        d2key[i] = kD2Init;
+        disp1s[i] = (int16_t)kInv;
+    }
+    __syncthreads();
+
+    const size_t rowoff = (size_t)y * W1 * WPC + lane * NPR;
+    const size_t vol = (size_t)H * W1 * WPC;
+    const uint32_t* C = reinterpret_cast<const uint32_t*>(frame_ptr(ws.C, ws_stride, f)) + rowoff;
+    uint32_t* Lv = reinterpret_cast<uint32_t*>(frame_ptr(ws.Lv, ws_stride, f)) + rowoff;
+    uint32_t* T = Lv + vol;  // Lv[1] doubles as the rendezvous scratch
+
+    uint32_t padmask[NPR];
+    make_padmask<NPR>(padmask, lane, d.D);
+    const uint32_t P1P1 = bcast16(d.P1), P2 = d.P2;
+    const int mid = W1 >> 1;
+    const int dirx = wid == 0 ? 1 : -1;
+    const int xa = wid == 0 ? 0 : W1 - 1;               // first cell of phase 1
+    const int n1 = wid == 0 ? mid : W1 - mid;           // cells in phase 1
+    const int n2 = W1 - n1;                             // cells in phase 2
+
+    PathState<NPR> s;
+    path_reset<NPR>(s);
+    // ---- phase 1: T = sat(L1 + L2 + L3 + own)
+    {
+        uint32_t cb[kHorPF][NPR], l1[kHorPF][NPR], l2[kHorPF][NPR], l3[kHorPF][NPR];
+#pragma unroll
+        for (int i = 0; i < kHorPF; i++)
+            if (i < n1) {
+                const size_t o = (size_t)(xa + dirx * i) * WPC;
+                ldv<NPR>(cb[i], C + o); ldv<NPR>(l1[i], Lv + o); ldv<NPR>(l2[i], Lv + vol + o); ldv<NPR>(l3[i], Lv + 2 * vol + o);
+            }
+        for (int k0 = 0; k0 < n1; k0 += kHorPF) {
+#pragma unroll
+            for (int i = 0; i < kHorPF; i++) {
+                const int k = k0 + i;
+                if (k < n1) {
+                    uint32_t c[NPR], sv[NPR];
+#pragma unroll
+                    for (int r = 0; r < NPR; r++) {
+                        c[r] = cb[i][r];
+                        sv[r] = __viaddmin_u16x2(__viaddmin_u16x2(l1[i][r], l2[i][r], kMaxC2), l3[i][r], kMaxC2);
+                    }
+                    if (k + kHorPF < n1) {
+                        const size_t o = (size_t)(xa + dirx * (k + kHorPF)) * WPC;
+                        ldv<NPR>(cb[i], C + o); ldv<NPR>(l1[i], Lv + o); ldv<NPR>(l2[i], Lv + vol + o); ldv<NPR>(l3[i], Lv + 2 * vol + o);
+                    }
+                    if (k == 0) path_start<NPR>(s, c, padmask);
+                    else path_step<NPR>(s, c, padmask, P1P1, P2, lane);
+#pragma unroll
+                    for (int r = 0; r < NPR; r++) sv[r] = __viaddmin_u16x2(sv[r], s.L[r], kMaxC2);
+                    stv<NPR>(T + (size_t)(xa + dirx * k) * WPC, sv);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- phase 2: S = sat(T_other + own) -> selection
+    {
+        const int xb = xa + dirx * n1;
+        uint32_t cb[kHorPF][NPR], tb[kHorPF][NPR];
+#pragma unroll
+        for (int i = 0; i < kHorPF; i++)
+            if (i < n2) {
+                const size_t o = (size_t)(xb + dirx * i) * WPC;
+                ldv<NPR>(cb[i], C + o); ldv<NPR>(tb[i], T + o);
+            }
+        for (int k0 = 0; k0 < n2; k0 += kHorPF) {
+#pragma unroll
+            for (int i = 0; i < kHorPF; i++) {
+                const int k = k0 + i;
+                if (k < n2) {
+                    uint32_t c[NPR], S[NPR];
+#pragma unroll
+                    for (int r = 0; r < NPR; r++) { c[r] = cb[i][r]; S[r] = tb[i][r]; }
+                    if (k + kHorPF < n2) {
+                        const size_t o = (size_t)(xb + dirx * (k + kHorPF)) * WPC;
+                        ldv<NPR>(cb[i], C + o); ldv<NPR>(tb[i], T + o);
+                    }
+                    if (n1 == 0 && k == 0) path_start<NPR>(s, c, padmask);
+                    else path_step<NPR>(s, c, padmask, P1P1, P2, lane);
+#pragma unroll
+                    for (int r = 0; r < NPR; r++) S[r] = __viaddmin_u16x2(S[r], s.L[r], kMaxC2);
+                    wta_cell<NPR>(S, lane, d, xb + dirx * k, disp1s, d2key);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- LR check (A.4.5)
+    int16_t* out = frame_ptr(ws.raw, ws_stride, f) + (size_t)y * W;
+    for (int x = threadIdx.x; x < W; x += blockDim.x) {
+        int d1 = disp1s[x];
+        if (d1 != kInv) {
+            const int _d = d1 >> 4, d_ = (d1 + 15) >> 4;
+            const int _x = x - _d, x_ = x - d_;
+            auto d2at = [&](int xx) -> int {
+                const uint32_t kk = d2key[xx];
+                return kk == kD2Init ? kInv : (int)(0xFFFFu - (kk & 0xFFFFu));
+            };
+            bool badl = false, badr = false;
+            if (_x >= 0 && _x < W) { const int v = d2at(_x); badl = v >= 0 && abs(v - _d) > d.disp12; }
+            if (x_ >= 0 && x_ < W) { const int v = d2at(x_); badr = v >= 0 && abs(v - d_) > d.disp12; }
+            if (badl && badr) d1 = kInv;
+        }
+        out[x] = (int16_t)d1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// A.4.6 post filters
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cswap(int& a, int& b) { const int t = min(a, b); b = max(a, b); a = t; }
+
+__global__ void k_median3(const int16_t* __restrict__ src, size_t src_stride, int16_t* __restrict__ dst, size_t dst_stride,
+                          int W, int H) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
+    if (x >= W) return;
+    const int16_t* s = frame_ptr(src, src_stride, f);
+    int16_t* o = frame_ptr(dst, dst_stride, f);
+    int v[9];
+#pragma unroll
+    for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+        for (int dx = -1; dx <= 1; dx++)
+            v[(dy + 1) * 3 + dx + 1] = s[(size_t)min(max(y + dy, 0), H - 1) * W + min(max(x + dx, 0), W - 1)];
+    // 19-exchange median-of-9 network
+    cswap(v[1], v[2]); cswap(v[4], v[5]); cswap(v[7], v[8]); cswap(v[0], v[1]); cswap(v[3], v[4]); cswap(v[6], v[7]);
+    cswap(v[1], v[2]); cswap(v[4], v[5]); cswap(v[7], v[8]); cswap(v[0], v[3]); cswap(v[5], v[8]); cswap(v[4], v[7]);
+    cswap(v[3], v[6]); cswap(v[1], v[4]); cswap(v[2], v[5]); cswap(v[4], v[7]); cswap(v[4], v[2]); cswap(v[6], v[4]);
+    cswap(v[4], v[2]);
+    o[(size_t)y * W + x] = (int16_t)v[4];
+}
+
+__device__ __forceinline__ int ccl_find(volatile int32_t* L, int i) {
+    int p = L[i];
+    while (p != i) { i = p; p = L[i]; }
+    return i;
+}
+__device__ __forceinline__ void ccl_union(int32_t* L, int a, int b) {
+    bool done;
+    do {
+        a = ccl_find(L, a);
+        b = ccl_find(L, b);
+        if (a < b) { const int old = atomicMin(&L[b], a); done = old == b; b = old; }
+        else if (b < a) { const int old = atomicMin(&L[a], b); done = old == a; a = old; }
+        else done = true;
+    } while (!done);
+}
+
+__global__ void k_ccl_init(const int16_t* __restrict__ img, int32_t* label, int32_t* csize, int n, size_t img_stride,
+                           size_t ws_stride) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, f = blockIdx.y;
+    if (i >= n) return;
+    frame_ptr(label, ws_stride, f)[i] = frame_ptr(img, img_stride, f)[i] != kInv ? i : -1;
+    frame_ptr(csize, ws_stride, f)[i] = 0;
+}
+__global__ void k_ccl_merge(const int16_t* __restrict__ img, int32_t* label, int W, int H, int maxDiff, size_t img_stride,
+                            size_t ws_stride) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
+    if (x >= W) return;
+    const int16_t* s = frame_ptr(img, img_stride, f);
+    int32_t* L = frame_ptr(label, ws_stride, f);
+    const int i = y * W + x;
+    const int v = s[i];
+    if (v == kInv) return;
+    if (x + 1 < W) { const int q = s[i + 1]; if (q != kInv && abs(v - q) <= maxDiff) ccl_union(L, i, i + 1); }
+    if (y + 1 < H) { const int q = s[i + W]; if (q != kInv && abs(v - q) <= maxDiff) ccl_union(L, i, i + W); }
+}
+__global__ void k_ccl_count(int32_t* label, int32_t* csize, int n, size_t ws_stride) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, f = blockIdx.y;
+    if (i >= n) return;
+    int32_t* L = frame_ptr(label, ws_stride, f);
+    if (L[i] < 0) return;
+    const int r = ccl_find(L, i);
+    L[i] = r;  // only ever lowers a label towards its root: concurrent finds stay valid
+    atomicAdd(&frame_ptr(csize, ws_stride, f)[r], 1);
+}
+__global__ void k_ccl_apply(const int16_t* __restrict__ img, const int32_t* __restrict__ label, const int32_t* __restrict__ csize,
+                            int16_t* __restrict__ out, int n, int maxSize, size_t img_stride, size_t ws_stride, size_t out_stride) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, f = blockIdx.y;
+    if (i >= n) return;
+    const int16_t v = frame_ptr(img, img_stride, f)[i];
+    const int32_t* L = frame_ptr(label, ws_stride, f);
+    int16_t o = v;
+    if (v != kInv) {
+        int r = L[i];
+        while (L[r] != r) r = L[r];
+        if (frame_ptr(csize, ws_stride, f)[r] <= maxSize) o = (int16_t)kInv;
+    }
+    frame_ptr(out, out_stride, f)[i] = o;
+}
+
+template <int NPR>
+int launch_paths(const SgbmDims& d, const SgbmWorkspace& ws, size_t ws_stride, int nb, cudaStream_t st) {
+    dim3 gv(cdiv(d.W1, 8), 3, nb);
+    { auto kern = k_sgbm_vert<NPR>; OVO_LAUNCH(kern, gv, dim3(256), 0, st, d, ws, ws_stride); }
+    OVO_LAUNCH_CHECK();
+    dim3 gh(d.H, nb);
+    const size_t smem = (size_t)d.W * 4 + (size_t)d.W * 2 + 16;
+    { auto kern = k_sgbm_horiz<NPR>; OVO_LAUNCH(kern, gh, dim3(64), smem, st, d, ws, ws_stride); }
+    OVO_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int SW2, int TX>
+int launch_cost(const SgbmDims& d, const SgbmWorkspace& ws, size_t ws_stride, int nb, cudaStream_t st) {
+    const int npairs = d.Dp / 2, upb = kCostThreads / npairs;
+    const int units = cdiv(d.W1, TX) * cdiv(d.H, kCostRS);
+    dim3 grid(cdiv(units, upb), 1, nb), block(npairs, upb);
+    { auto kern = k_sgbm_cost<SW2, TX>; OVO_LAUNCH(kern, grid, block, 0, st, d, ws, ws_stride); }
+    OVO_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace
+
+size_t sgbm_workspace_bytes(const SgbmDims& d) {
+    const size_t vol = align_up((size_t)d.H * d.W1 * d.Dp * 2, 256);
+    const size_t img = align_up((size_t)d.H * d.W * 4, 256);
+    return align_up(4 * img /*prep*/ + 4 * vol /*C + Lv[3]*/ + 4 * img /*raw, med (i16) + label, csize (i32) -> 2*0.5+2 = 3 img*/, 256);
+}
+
+void sgbm_carve(const SgbmDims& d, uint8_t* base, SgbmWorkspace* ws) {
+    const size_t vol = align_up((size_t)d.H * d.W1 * d.Dp * 2, 256);
+    const size_t img = align_up((size_t)d.H * d.W * 4, 256);
+    uint8_t* p = base;
+    ws->prep = reinterpret_cast<uint32_t*>(p); p += 4 * img;
+    ws->C = reinterpret_cast<int16_t*>(p); p += vol;
+    ws->Lv = reinterpret_cast<int16_t*>(p); p += 3 * vol;
+    ws->raw = reinterpret_cast<int16_t*>(p); p += img / 2;
+    ws->med = reinterpret_cast<int16_t*>(p); p += img / 2;
+    ws->label = reinterpret_cast<int32_t*>(p); p += img;
+    ws->csize = reinterpret_cast<int32_t*>(p); p += img;
+}
+
+int sgbm_launch(const SgbmDims& d, const SgbmWorkspace* ws0, size_t ws_stride, int nb, const uint8_t* left, const uint8_t* right,
+                int pitch, size_t frame_stride, int16_t* disp_out, cudaStream_t st) {
+    const SgbmWorkspace& ws = *ws0;
+    {
+        dim3 grid(cdiv(d.W, 128), d.H, nb * 2);
+        OVO_LAUNCH(k_sgbm_prep, grid, dim3(128), 0, st, left, right, pitch, frame_stride, d, ws, ws_stride);
+        OVO_LAUNCH_CHECK();
+    }
+    int rc;
+    switch (d.bs) {
+        case 3: rc = launch_cost<1, 16>(d, ws, ws_stride, nb, st); break;
+        case 5: rc = launch_cost<2, 16>(d, ws, ws_stride, nb, st); break;
+        case 7: rc = launch_cost<3, 8>(d, ws, ws_stride, nb, st); break;
+        case 9: rc = launch_cost<4, 8>(d, ws, ws_stride, nb, st); break;
+        case 11: rc = launch_cost<5, 8>(d, ws, ws_stride, nb, st); break;
+        default: set_error("blockSize %d unsupported (3,5,7,9,11)", d.bs); return 1;
+    }
+    if (rc) return rc;
+    switch (d.Dp) {
+        case 64: rc = launch_paths<1>(d, ws, ws_stride, nb, st); break;
+        case 128: rc = launch_paths<2>(d, ws, ws_stride, nb, st); break;
+        case 256: rc = launch_paths<4>(d, ws, ws_stride, nb, st); break;
+        default: set_error("padded disparity range %d unsupported", d.Dp); return 1;
+    }
+    if (rc) return rc;
+    const int n = d.W * d.H;
+    const size_t out_stride = (size_t)n * 2;
+    dim3 gimg(cdiv(d.W, 128), d.H, nb);
+    if (d.speckleWin <= 0) {
+        OVO_LAUNCH(k_median3, gimg, dim3(128), 0, st, ws.raw, ws_stride, disp_out, out_stride, d.W, d.H);
+        OVO_LAUNCH_CHECK();
+        return 0;
+    }
+    OVO_LAUNCH(k_median3, gimg, dim3(128), 0, st, ws.raw, ws_stride, ws.med, ws_stride, d.W, d.H);
+    OVO_LAUNCH_CHECK();
+    dim3 glin(cdiv(n, 256), nb);
+    OVO_LAUNCH(k_ccl_init, glin, dim3(256), 0, st, ws.med, ws.label, ws.csize, n, ws_stride, ws_stride);
+    OVO_LAUNCH_CHECK();
+    OVO_LAUNCH(k_ccl_merge, gimg, dim3(128), 0, st, ws.med, ws.label, d.W, d.H, d.speckleDiff, ws_stride, ws_stride);
+    OVO_LAUNCH_CHECK();
+    OVO_LAUNCH(k_ccl_count, glin, dim3(256), 0, st, ws.label, ws.csize, n, ws_stride);
+    OVO_LAUNCH_CHECK();
+    OVO_LAUNCH(k_ccl_apply, glin, dim3(256), 0, st, ws.med, ws.label, ws.csize, disp_out, n, d.speckleWin, ws_stride, ws_stride, out_stride);
+    OVO_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace ovo
