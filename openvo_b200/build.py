@@ -38,7 +38,7 @@ def build(force=False, verbose=False):
             if verbose:
                 print(r.stderr)
     if force or _stale(LIB, objs):
-        subprocess.check_call([nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"])
+        subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + ["-lcudart"])
     return LIB
 
 

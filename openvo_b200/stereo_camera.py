@@ -1,0 +1,127 @@
+"""StereoCamera — same constructor, attributes and methods as the reference class
+(ref: src/openVO/stereo_camera.py:6-55), with the per-frame arithmetic on the B200.
+
+Calibration (stereoRectify / initUndistortRectifyMap) is init-time only and stays a cv2 call, exactly as in the
+reference (out of the hot path).  ``compute_3d`` keeps the reference's contract — it returns numpy
+arrays cropped with the (x, y, w, h)-as-(x1, y1, x2, y2) slices (bug-compatible B1) — while StereoOdometer uses the
+device-resident path (``frames_device``) and never materialises the 3-D image.
+"""
+import pickle
+
+import numpy as np
+
+from . import _native as N
+
+
+class _SgbmHandle:
+    """Stands in for the cv2.StereoSGBM object the reference keeps in ``stereoSGBM``
+    (ref: src/openVO/stereo_camera.py:23-27): ``compute(left, right)`` -> int16 disparity * 16."""
+
+    def __init__(self, cam):
+        self._cam = cam
+
+    def compute(self, left, right):
+        cam = self._cam
+        left, right = np.asarray(left), np.asarray(right)
+        if left.shape != right.shape or left.dtype != np.uint8 or right.dtype != np.uint8 or left.ndim != 2:
+            raise ValueError("StereoSGBM.compute: left and right must be 2-D uint8 images of equal size "
+                             "(the reference raises cv2.error here)")
+        if left.shape != (cam.img_size[1], cam.img_size[0]):
+            raise ValueError("StereoSGBM.compute: image size differs from the camera's img_size")
+        eng = cam.engine()
+        l, r = eng.upload(left[None], "sgbm_l"), eng.upload(right[None], "sgbm_r")
+        return eng.sgbm(l, r)[0].cpu().numpy()
+
+    def __getattr__(self, name):
+        # getMinDisparity(), getNumDisparities(), ... like the cv2 object
+        if name.startswith("get"):
+            key = name[3].lower() + name[4:]
+            key = {"p1": "P1", "p2": "P2"}.get(key, key)
+            p = self._cam.sgbm_params
+            if key in p:
+                return lambda: p[key]
+            if key == "mode":
+                return lambda: 0  # MODE_SGBM
+        raise AttributeError(name)
+
+
+class StereoCamera:
+    @classmethod
+    def from_pfiles(cls, left_cam_file, right_cam_file, rect_file, sgbm_file, img_size):
+        # ref: src/openVO/stereo_camera.py:7-14
+        loaded = []
+        for path in (left_cam_file, right_cam_file, rect_file, sgbm_file):
+            with open(path, "rb") as fh:
+                loaded.append(pickle.load(fh))
+        cam_l, cam_r, rect, sgbm = loaded
+        return cls(cam_l["K"], cam_l["dist"], cam_r["K"], cam_r["dist"], rect, sgbm, img_size)
+
+    def __init__(self, K_left, dist_left, K_right, dist_right, rect_params, sgbm_params, img_size):
+        import cv2  # init-time calibration only (ref: src/openVO/stereo_camera.py:17-22)
+        R1, R2, P1, P2, self.Q, self.valid_region_left, self.valid_region_right = cv2.stereoRectify(
+            K_left, dist_left, K_right, dist_right, img_size, rect_params["R"], rect_params["T"])
+        self.map_left_1, self.map_left_2 = cv2.initUndistortRectifyMap(K_left, dist_left, R1, P1, img_size, cv2.CV_16SC2)
+        self.map_right_1, self.map_right_2 = cv2.initUndistortRectifyMap(K_right, dist_right, R2, P2, img_size, cv2.CV_16SC2)
+        self.img_size = (int(img_size[0]), int(img_size[1]))
+        self.sgbm_params = {k: int(sgbm_params[k]) for k in N.SGBM_KEYS}
+        self.stereoSGBM = _SgbmHandle(self)
+        self._engines = {}
+
+    # ---- device engine (one per (nfeatures, batch, mask range)) -------------------------------------------------------
+    def engine(self, nfeatures=500, max_batch=1, min_valid=4.0, max_valid=100.0, lib_path=None):
+        from .engine import Engine
+        key = (int(nfeatures), int(max_batch), float(min_valid), float(max_valid))
+        eng = self._engines.get(key)
+        if eng is None:
+            eng = Engine(self.img_size[0], self.img_size[1], self.sgbm_params, self.valid_region_left, self.Q, nfeatures,
+                         max_batch, min_valid, max_valid, lib_path=lib_path)
+            self._engines[key] = eng
+        return eng
+
+    # ---- reference API ---------------------------------------------------------------------------------------------------
+    def undistort_rectify_left(self, img):
+        return self._remap(img, self.map_left_1, self.map_left_2)
+
+    def undistort_rectify_right(self, img):
+        return self._remap(img, self.map_right_1, self.map_right_2)
+
+    def _remap(self, img, map1, map2):
+        raise NotImplementedError(
+            "openvo_b200: cv2.remap rectification (ref: src/openVO/stereo_camera.py:29-33) is a SURVEY.md §8(f) 'next' row "
+            "and is not on the device yet; pass rectified frames with preprocessed=True / preprocessed_frames=True")
+
+    def crop_to_valid_region_left(self, img):
+        r = self.valid_region_left
+        return img[r[1]:r[3], r[0]:r[2]]
+
+    def crop_to_valid_region_right(self, img):
+        r = self.valid_region_right
+        return img[r[1]:r[3], r[0]:r[2]]
+
+    def _gray(self, img):
+        img = np.asarray(img)
+        if img.ndim == 3:
+            raise NotImplementedError(
+                "openvo_b200: cv2.cvtColor(BGR2GRAY) (ref: src/openVO/stereo_camera.py:44-47) is a SURVEY.md §8(f) 'next' "
+                "row and is not on the device yet; pass grayscale frames")
+        return img
+
+    def _prepare(self, img_left, img_right, preprocessed):
+        img_left, img_right = self._gray(img_left), self._gray(img_right)
+        if not preprocessed:
+            img_left = self.undistort_rectify_left(img_left)
+            img_right = self.undistort_rectify_right(img_right)
+        if img_left.shape != img_right.shape or img_left.dtype != np.uint8 or img_right.dtype != np.uint8:
+            raise ValueError("left and right must be uint8 images of equal size (the reference raises cv2.error here)")
+        if img_left.shape != (self.img_size[1], self.img_size[0]):
+            raise ValueError("image size differs from the camera's img_size")
+        return img_left, img_right
+
+    def compute_3d(self, img_left, img_right, preprocessed=False):
+        """ref: src/openVO/stereo_camera.py:43-55 -> (img_3d f32 H'xW'x3, disparity f32 H'xW', img_left u8 H'xW')."""
+        img_left, img_right = self._prepare(img_left, img_right, preprocessed)
+        eng = self.engine()
+        l, r = eng.upload(img_left[None], "c3d_l"), eng.upload(img_right[None], "c3d_r")
+        disp, _ = eng.disparity_post(eng.sgbm(l, r))
+        xyz = eng.reproject(disp[0])
+        return xyz.cpu().numpy(), disp[0].cpu().numpy(), self.crop_to_valid_region_left(img_left)

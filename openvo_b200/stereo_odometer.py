@@ -1,0 +1,283 @@
+"""StereoOdometer — same constructor, constants, attributes and per-frame ``update`` as the reference class
+(ref: src/openVO/stereo_odometer.py:4-226), with every per-frame stage on the B200.
+
+``update`` keeps all frame products on the device (disparity, keypoints, descriptors; the 3-D image is never
+materialised: the point lookup reprojects on the fly) and reads back 144 bytes per frame pair.  The reference's
+public state (``current_kps`` as cv2.KeyPoint tuples, ``current_3d`` as an HxWx3 float image, ...) is materialised
+lazily when read.  Control flow — the skip / fall-back state machine B4 — is host Python exactly as in the reference.
+"""
+import numpy as np
+
+from . import _native as N
+
+
+def _keypoints(kp):
+    import cv2
+    return tuple(cv2.KeyPoint(float(r[0]), float(r[1]), float(r[2]), float(r[3]), float(r[4]), int(r[5]), -1) for r in kp)
+
+
+class _OrbHandle:
+    """Stands in for the cv2.ORB object in ``StereoOdometer.orb`` (ref: src/openVO/stereo_odometer.py:22,117)."""
+
+    def __init__(self, od):
+        self._od = od
+
+    def detectAndCompute(self, image, mask=None):
+        eng = self._od._engine()
+        image = np.asarray(image)
+        if image.dtype != np.uint8 or image.shape != (eng.ch, eng.cw):
+            raise ValueError("ORB: expected a uint8 image of the camera's cropped size %dx%d" % (eng.cw, eng.ch))
+        img = eng.upload(image[None], "orb_img")
+        m = None
+        if mask is not None:
+            mask = np.asarray(mask)
+            if mask.dtype != np.uint8 or mask.shape != image.shape:
+                raise ValueError("ORB: mask must be uint8 and of the image's size")
+            m = eng.upload(mask[None], "orb_mask")
+        kp, desc, n = eng.orb(img, m)
+        if n[0] == 0:
+            return (), None
+        return _keypoints(kp[0, :n[0]].cpu().numpy()), desc[0, :n[0]].cpu().numpy()
+
+    def getMaxFeatures(self):
+        return self._od._nfeatures
+
+
+class _MatcherHandle:
+    """Stands in for cv2.BFMatcher(NORM_HAMMING) in ``StereoOdometer.matcher`` (ref: stereo_odometer.py:22,163)."""
+
+    def __init__(self, od):
+        self._od = od
+
+    def knnMatch(self, queryDescriptors, trainDescriptors, k=2):
+        import cv2
+        import torch
+        if k != 2:
+            raise ValueError("only k=2 is on the hot path")
+        eng = self._od._engine()
+        q = np.ascontiguousarray(queryDescriptors, np.uint8)
+        t = np.ascontiguousarray(trainDescriptors, np.uint8)
+        nn = torch.empty((len(q), 4), dtype=torch.int32, device=eng.device)
+        eng.knn2(torch.from_numpy(q).to(eng.device), len(q), torch.from_numpy(t).to(eng.device), len(t), out=nn)
+        out = []
+        for i, (i0, d0, i1, d1) in enumerate(nn.cpu().numpy().tolist()):
+            row = []
+            if i0 >= 0:
+                row.append(cv2.DMatch(i, i0, 0, float(d0)))
+            if i1 >= 0:
+                row.append(cv2.DMatch(i, i1, 0, float(d1)))
+            out.append(tuple(row))
+        return tuple(out)
+
+
+class StereoOdometer:
+    # ref: src/openVO/stereo_odometer.py:6-12 (read through ``self.`` so subclass / instance overrides work)
+    MIN_VALID_DISPARITY = 4
+    MAX_VALID_DISPARITY = 100
+    MAX_DISTANCE_CHANGE = 1
+    MAX_ROTATION_CHANGE = np.pi / 3
+
+    def __init__(self, stereo_camera, nfeatures=500, match_threshold=0.8, rigidity_threshold=0, outlier_threshold=0,
+                 preprocessed_frames=False, min_matches=10):
+        self.stereo = stereo_camera
+        self._nfeatures = nfeatures
+        self._cur = None   # last committed frame (device resident)
+        self._prev = None  # the one before
+        self.orb, self.matcher = _OrbHandle(self), _MatcherHandle(self)
+        self.match_threshold, self.rigidity_threshold = match_threshold, rigidity_threshold
+        self.outlier_threshold, self.preprocessed_frames = outlier_threshold, preprocessed_frames
+        self.min_matches = min_matches
+        self.skipped_frames = 0
+        self.c_T_w = np.eye(4)
+        self.c_T_w_prev = np.eye(4)
+        self.skip_cause = ""
+        self.last_match_count = 0
+
+    def _engine(self):
+        return self.stereo.engine(self._nfeatures, 1, float(self.MIN_VALID_DISPARITY), float(self.MAX_VALID_DISPARITY))
+
+    # ---- lazily materialised public state (reference types) --------------------------------------------------------------
+    def _host(self, frame, what):
+        if frame is None:
+            return None
+        h = frame._host
+        if what not in h:
+            if what == "img":
+                h[what] = frame.img.cpu().numpy()
+            elif what == "disparity":
+                h[what] = frame.disp.cpu().numpy()
+            elif what == "3d":
+                h[what] = self._engine().reproject(frame.disp).cpu().numpy()
+            elif what == "kp_array":
+                h[what] = frame.kp[:frame.n_kp].cpu().numpy()
+            elif what == "kps":
+                h[what] = _keypoints(self._host(frame, "kp_array"))
+            elif what == "desc":
+                h[what] = frame.desc[:frame.n_kp].cpu().numpy()
+        return h[what]
+
+    current_img = property(lambda self: self._host(self._cur, "img"))
+    current_disparity = property(lambda self: self._host(self._cur, "disparity"))
+    current_3d = property(lambda self: self._host(self._cur, "3d"))
+    current_kps = property(lambda self: self._host(self._cur, "kps"))
+    current_desc = property(lambda self: self._host(self._cur, "desc"))
+    prev_img = property(lambda self: self._host(self._prev, "img"))
+    prev_disparity = property(lambda self: self._host(self._prev, "disparity"))
+    prev_3d = property(lambda self: self._host(self._prev, "3d"))
+    prev_kps = property(lambda self: self._host(self._prev, "kps"))
+    prev_desc = property(lambda self: self._host(self._prev, "desc"))
+
+    # ---- helpers that are part of the reference's method surface --------------------------------------------------------
+    def feature_mask(self, disparity):
+        # ref: src/openVO/stereo_odometer.py:38-41 (the hot path fuses this into ovo_disparity_post)
+        ok = (disparity >= self.MIN_VALID_DISPARITY) * (disparity <= self.MAX_VALID_DISPARITY)
+        return ok.astype(np.uint8) * 255
+
+    def valid_distance_change(self, prev_kp_idx, current_kp_idx):
+        # ref: src/openVO/stereo_odometer.py:43-48 (dead code in the reference: guarded by ``if (False)``)
+        px, py = self.prev_kps[prev_kp_idx].pt
+        cx, cy = self.current_kps[current_kp_idx].pt
+        gap = np.linalg.norm(self.prev_3d[int(py)][int(px)]) - np.linalg.norm(self.current_3d[int(cy)][int(cx)])
+        return gap <= self.MAX_DISTANCE_CHANGE * (self.skipped_frames + 1)
+
+    def bilinear_interpolate_pixels(self, img, x, y):
+        # ref: src/openVO/stereo_odometer.py:50-79, host helper for callers that hold a numpy 3-D image; ``update`` uses the
+        # fused device lookup (ovo_match_points) instead.
+        fx, fy = int(x), int(y)
+        h, w = img.shape[0:2]
+        rx, ry = x - fx, y - fy
+        num, den = 0, 0
+        for px, py, wt in ((fx, fy, (1 - rx) * (1 - ry)), (fx, fy + 1, (1 - rx) * ry), (fx + 1, fy, rx * (1 - ry)),
+                           (fx + 1, fy + 1, rx * ry)):
+            if px < w and py < h and not np.isinf(img[py, px]).any():
+                num = num + wt * img[py, px]
+                den = den + wt
+        return num / den
+
+    def save_frame_update(self, frame):
+        # ref: src/openVO/stereo_odometer.py:107-113
+        self._prev, self._cur = self._cur, frame
+
+    # ---- the per-frame call --------------------------------------------------------------------------------------------------
+    def update(self, img_left, img_right):
+        """ref: src/openVO/stereo_odometer.py:115-160."""
+        left, right = self.stereo._prepare(img_left, img_right, self.preprocessed_frames)
+        eng = self._engine()
+        frame = eng.frames(eng.upload(left[None], "upd_l"), eng.upload(right[None], "upd_r"))[0]
+        if frame.n_kp < self.min_matches:
+            self.skipped_frames += 1
+            self.skip_cause = "keypoints"
+            return False
+        if self._cur is None:
+            self.save_frame_update(frame)
+            return True
+        T = self._relative(self._cur, frame)
+        if T is not None:
+            self.c_T_w_prev = self.c_T_w
+            self.c_T_w = T @ self.c_T_w
+        if T is None and self._prev is not None:
+            T = self._relative(self._prev, frame)
+            if T is not None:
+                older = self.c_T_w_prev
+                self.c_T_w_prev = self.c_T_w
+                self.c_T_w = T @ older
+                self.skipped_frames = 0
+        if T is None:
+            self.skipped_frames += 1
+            return False
+        self.skipped_frames = 0
+        self.save_frame_update(frame)
+        return True
+
+    def _relative(self, a, b):
+        """point_clouds + point_cloud_transform for device frames a -> b."""
+        eng = self._engine()
+        if b.n_kp < 2:
+            raise IndexError("tuple index out of range")  # the reference indexes m[1] (ref: stereo_odometer.py:164)
+        n, bad, out = eng.pair(a, b, self.match_threshold)
+        self.last_match_count = n
+        if n < self.min_matches:
+            self.skip_cause = "matches"
+            return None
+        if bad:
+            raise ZeroDivisionError("division by zero")  # ref: stereo_odometer.py:79 with every tap skipped
+        if self.rigidity_threshold > 0 or self.outlier_threshold > 0:
+            return self.point_cloud_transform(eng.pts1[:n].cpu().numpy(), eng.pts2[:n].cpu().numpy())
+        if n < 10:
+            self.skip_cause = "rigidity"
+        return self._gate(out)
+
+    def _gate(self, out):
+        # ref: src/openVO/stereo_odometer.py:204-223
+        T = np.eye(4)
+        T[:3, :4] = out[:12].reshape(3, 4)
+        if np.isnan(T).any():
+            self.skip_cause = "nan"
+            return None
+        k = self.skipped_frames + 1
+        far = np.linalg.norm(T[0:3, 3]) > self.MAX_DISTANCE_CHANGE * k
+        spun = out[13] > self.MAX_ROTATION_CHANGE * k
+        if far:
+            self.skip_cause = "bigdist"
+        if spun:
+            self.skip_cause = "bigrot"
+        return None if (far or spun) else T
+
+    def point_clouds(self, kps1, kps2, desc1, desc2, im3d1, im3d2):
+        """ref: src/openVO/stereo_odometer.py:162-175 for callers that hold host-side products."""
+        matches = self.matcher.knnMatch(desc1, desc2, k=2)
+        matches = [m[0] for m in matches if m[0].distance < self.match_threshold * m[1].distance]
+        if len(matches) < self.min_matches:
+            return None, None
+        pts1 = [self.bilinear_interpolate_pixels(im3d1, *kps1[m.queryIdx].pt) for m in matches]
+        pts2 = [self.bilinear_interpolate_pixels(im3d2, *kps2[m.trainIdx].pt) for m in matches]
+        return np.array(pts1), np.array(pts2)
+
+    def rigid_body_filter(self, prev_pts, pts):
+        """ref: src/openVO/stereo_odometer.py:82-105 (off by default; SURVEY.md §8(f) n3 — host numpy for now)."""
+        d_now = np.linalg.norm(pts[:, None, :] - pts[None, :, :], axis=2)
+        d_old = np.linalg.norm(prev_pts[:, None, :] - prev_pts[None, :, :], axis=2)
+        consistency = (np.abs(d_now - d_old) < self.rigidity_threshold).astype(int)
+        clique = np.zeros(len(pts), int)
+        degree = consistency.sum(0)
+        first = int(np.argmax(degree))
+        clique[first] = 1
+        compatible = consistency[first]
+        for _ in range(len(pts)):
+            cand = (compatible - clique).astype(int)
+            if cand.sum() == 0:
+                break
+            clique[int(np.argmax(degree * cand))] = 1
+            compatible = (consistency @ clique >= clique.sum()).astype(int)
+        return clique
+
+    def _rigid(self, a, b):
+        out = self._engine().rigid(a, b)
+        return out
+
+    def point_cloud_transform(self, current_pts, next_pts):
+        """ref: src/openVO/stereo_odometer.py:177-223."""
+        if self.rigidity_threshold > 0:
+            inl = self.rigid_body_filter(current_pts, next_pts)
+            current_pts, next_pts = current_pts[inl > 0], next_pts[inl > 0]
+        rigidity_cause = False
+        if len(current_pts) < 10:
+            rigidity_cause = True
+            self.skip_cause = "rigidity"
+        if self.outlier_threshold > 0 and len(current_pts) >= 10:
+            T = np.eye(4)
+            T[:3, :4] = self._rigid(current_pts, next_pts)[:12].reshape(3, 4)
+            hn = np.hstack([next_pts, np.ones((len(next_pts), 1))])
+            hp = np.hstack([current_pts, np.ones((len(current_pts), 1))])
+            err = np.linalg.norm(hn - hp @ T.T, axis=1) / np.linalg.norm(hn, axis=1)
+            thr = self.outlier_threshold + np.median(err)
+            current_pts, next_pts = current_pts[err < thr], next_pts[err < thr]
+        if len(current_pts) < self.min_matches:
+            if not rigidity_cause:
+                self.skip_cause = "outlier"
+            return None
+        return self._gate(self._rigid(current_pts, next_pts))
+
+    def current_pose(self):
+        # ref: src/openVO/stereo_odometer.py:225-226
+        return np.linalg.inv(self.c_T_w)
