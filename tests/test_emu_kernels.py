@@ -1,0 +1,139 @@
+"""CPU tier: the CUDA sources compiled against tests/emu/cuda_emu.h (a fiber-based execution emulator) and driven through
+the same C ABI, checked bit-exactly against the oracle.  This exercises the kernels' indexing / warp-collective / packed
+arithmetic logic without a GPU; the real parity tests are the -m gpu ones."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, block_mask, occluded_pair, sgbm_params
+from openvo_b200 import _native as N
+from openvo_b200 import synth
+from oracle import openvo_port as O
+
+sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+
+
+@pytest.fixture(scope="module")
+def emu():
+    import build_emu
+    return N.load(build_emu.build())
+
+
+class Ctx:
+    def __init__(self, lib, W, H, params, roi, Q, n, nb=1):
+        self.lib = lib
+        self.cfg = N.make_config(W, H, params, roi, Q, n, max_batch=nb)
+        nbytes = lib.ovo_workspace_bytes(ctypes.byref(self.cfg))
+        assert nbytes, lib.ovo_last_error()
+        self.ws = np.zeros(nbytes + 256, np.uint8)
+        off = (-self.ws.ctypes.data) % 256
+        self.ctx = lib.ovo_create(ctypes.byref(self.cfg), self.ws.ctypes.data + off, nbytes)
+        assert self.ctx, lib.ovo_last_error()
+        self.cap = lib.ovo_kp_capacity(ctypes.byref(self.cfg))
+        cw, ch = ctypes.c_int(), ctypes.c_int()
+        lib.ovo_cropped_size(ctypes.byref(self.cfg), ctypes.byref(cw), ctypes.byref(ch))
+        self.cw, self.ch = cw.value, ch.value
+
+    def __del__(self):
+        self.lib.ovo_destroy(self.ctx)
+
+
+@pytest.mark.parametrize("W,H,D,nb,kw", [
+    (160, 40, 32, 1, {}),
+    (200, 36, 64, 1, dict(blockSize=3, P1=72, P2=288, uniquenessRatio=0, speckleWindowSize=0)),
+    (150, 40, 48, 1, dict(blockSize=7, preFilterCap=15, uniquenessRatio=15, disp12MaxDiff=2, speckleWindowSize=50, speckleRange=1)),
+    (200, 34, 128, 2, {}),
+])
+def test_sgbm_kernels(emu, W, H, D, nb, kw):
+    p = sgbm_params(D, **kw)
+    L, R = occluded_pair(W, H)
+    Ls = np.stack([np.roll(L, 3 * i, 1) for i in range(nb)])
+    Rs = np.stack([np.roll(R, 3 * i, 1) for i in range(nb)])
+    c = Ctx(emu, W, H, p, (0, 0, W, H), np.eye(4), 100, nb)
+    out = np.zeros((nb, H, W), np.int16)
+    N.check(emu, emu.ovo_sgbm_compute(c.ctx, N.ptr(Ls), N.ptr(Rs), W, W * H, nb, N.ptr(out), None))
+    for f in range(nb):
+        assert np.array_equal(out[f], O.sgbm_compute(Ls[f], Rs[f], p))
+
+
+@pytest.mark.parametrize("W,H,n,usemask,nb", [(320, 120, 300, False, 1), (300, 170, 300, True, 2)])
+def test_orb_kernels(emu, W, H, n, usemask, nb):
+    c = Ctx(emu, W, H, sgbm_params(16), (0, 0, W, H), np.eye(4), n, nb)
+    L, R = synth.kat_pair(W, H)
+    imgs = np.stack([L, R][:nb])
+    mask = np.stack([block_mask(H, W)] * nb) if usemask else None
+    kp = np.zeros((nb, c.cap, 6), np.float32)
+    desc = np.zeros((nb, c.cap, 32), np.uint8)
+    nk = (ctypes.c_int * nb)()
+    N.check(emu, emu.ovo_orb_detect_compute(c.ctx, N.ptr(imgs), N.ptr(mask), nb, N.ptr(kp), N.ptr(desc), nk, None))
+    for f in range(nb):
+        rk, rd = O.orb_detect_compute(imgs[f], None if mask is None else mask[f], n)
+        assert nk[f] == len(rk) and np.array_equal(kp[f, :nk[f]], rk) and np.array_equal(desc[f, :nk[f]], rd)
+
+
+def test_match_and_pose_kernels(emu):
+    rng = np.random.default_rng(3)
+    W, H, n = 300, 150, 300
+    Q = np.array([[1, 0, 0, -(W - 1) / 2], [0, 1, 0, -(H - 1) / 2], [0, 0, 0, 300.0], [0, 0, 1 / 0.537, 0.0]]) + rng.normal(0, 1e-3, (4, 4))
+    roi = (2, 3, W - 1, H - 2)
+    c = Ctx(emu, W, H, sgbm_params(32), roi, Q, n)
+    # 2-NN with ties
+    for nq, nt in ((1, 1), (5, 2), (300, 257)):
+        q = rng.integers(0, 256, (nq, 32), dtype=np.uint8) & 0xF0
+        t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+        t[nt // 2:] &= 0xF0
+        nn = np.zeros((nq, 4), np.int32)
+        N.check(emu, emu.ovo_knn2_hamming(c.ctx, N.ptr(q), nq, N.ptr(t), nt, N.ptr(nn), None))
+        assert np.array_equal(nn, O.knn2_hamming(q, t))
+    # disparity post + reprojection
+    d16 = rng.integers(-1, 1600, (H, W)).astype(np.int16)
+    d16[rng.random((H, W)) < 0.1] = -16
+    d16[rng.random((H, W)) < 0.05] = 0
+    df = np.zeros((c.ch, c.cw), np.float32)
+    mk = np.zeros((c.ch, c.cw), np.uint8)
+    N.check(emu, emu.ovo_disparity_post(c.ctx, N.ptr(d16), 1, N.ptr(df), N.ptr(mk), None))
+    full = d16.astype(np.float32) / 16
+    crop = full[roi[1]:roi[3], roi[0]:roi[2]]
+    assert np.array_equal(df, crop) and np.array_equal(mk, ((crop >= 4) * (crop <= 100)).astype(np.uint8) * 255)
+    xyz = np.zeros((c.ch, c.cw, 3), np.float32)
+    N.check(emu, emu.ovo_reproject_3d(c.ctx, N.ptr(df), N.ptr(xyz), None))
+    ref3 = O.reproject_to_3d(full, Q)[roi[1]:roi[3], roi[0]:roi[2]]
+    assert np.array_equal(xyz.view(np.uint32), ref3.view(np.uint32))
+    # ratio + ordered compaction + fused lookup
+    nq, nt = 200, 180
+    kp1, kp2 = np.zeros((nq, 6), np.float32), np.zeros((nt, 6), np.float32)
+    for kp, m in ((kp1, nq), (kp2, nt)):
+        kp[:, 0] = rng.uniform(0, c.cw - 0.01, m)
+        kp[:, 1] = rng.uniform(0, c.ch - 0.01, m)
+    kp1[:30, :2] = np.floor(kp1[:30, :2])
+    kp1[0, :2] = (c.cw - 1, c.ch - 1)
+    q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+    t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+    t[:100] = q[:100] ^ (rng.random((100, 32)) < 0.05).astype(np.uint8)
+    nn = np.zeros((nq, 4), np.int32)
+    N.check(emu, emu.ovo_knn2_hamming(c.ctx, N.ptr(q), nq, N.ptr(t), nt, N.ptr(nn), None))
+    matches, p1, p2, cnt = np.zeros((nq, 3), np.int32), np.zeros((nq, 3), np.float32), np.zeros((nq, 3), np.float32), np.zeros(2, np.int32)
+    N.check(emu, emu.ovo_match_points(c.ctx, N.ptr(nn), nq, 0.8, N.ptr(kp1), N.ptr(kp2), N.ptr(df), N.ptr(df), N.ptr(matches),
+                                     N.ptr(p1), N.ptr(p2), N.ptr(cnt), None))
+    keep = [i for i in range(nq) if float(nn[i, 1]) < 0.8 * float(nn[i, 3])]
+    assert cnt[0] == len(keep) >= 90 and np.array_equal(matches[:cnt[0], 0], keep)
+    with np.errstate(all="ignore"):
+        for j, i in enumerate(keep):
+            a = O.bilinear_lookup(ref3, float(kp1[i, 0]), float(kp1[i, 1]))
+            b = O.bilinear_lookup(ref3, float(kp2[nn[i, 0], 0]), float(kp2[nn[i, 0], 1]))
+            assert np.array_equal(a.view(np.uint32), p1[j].view(np.uint32)) or np.isnan(a).any()
+            assert np.array_equal(b.view(np.uint32), p2[j].view(np.uint32)) or np.isnan(b).any()
+    # Umeyama
+    src = rng.normal(0, 5, (150, 3)).astype(np.float32)
+    ang = 0.04
+    Rm = np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]])
+    dst = (src @ Rm.T + [0.1, -0.02, 0.5] + rng.normal(0, 0.01, (150, 3))).astype(np.float32)
+    out = np.zeros(16)
+    m = np.array([150], np.int32)
+    N.check(emu, emu.ovo_rigid_transform(c.ctx, N.ptr(src), N.ptr(dst), N.ptr(m), 150, N.ptr(out), None))
+    T, s = O.umeyama(src, dst)
+    assert np.abs(out[:12].reshape(3, 4) - T).max() < 1e-12 and abs(out[12] - s) < 1e-12
+    assert abs(out[13] - O.rotation_angle(T[:, :3])) < 1e-10 and abs(out[14] - np.linalg.norm(T[:, 3])) < 1e-12

@@ -1,0 +1,178 @@
+"""GPU tier (-m gpu): the CUDA path, called through the C ABI, against the oracle and the reference-generated fixtures.
+Bit-exact for disparity / keypoints / descriptors / matches; poses within 1e-4 rad and 1e-3 relative translation
+(BASELINE.json north_star) — in practice ~1e-14."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import SGBM_CASES, block_mask, occluded_pair, sgbm_params
+from openvo_b200 import StereoCamera, StereoOdometer, synth
+from oracle import openvo_port as O
+
+pytestmark = pytest.mark.gpu
+ROT_TOL, TRANS_REL_TOL = 1e-4, 1e-3
+
+
+def _cam(W, H, D, **kw):
+    args = synth.camera_args(W, H, D)
+    args["sgbm_params"].update(kw)
+    return StereoCamera(**args), args
+
+
+def _pose_close(T, Tref):
+    dR = T[:3, :3] @ Tref[:3, :3].T
+    ang = np.arccos(np.clip((np.trace(dR) - 1) / 2, -1, 1))
+    dt = np.linalg.norm(T[:3, 3] - Tref[:3, 3])
+    return ang <= ROT_TOL and dt <= TRANS_REL_TOL * max(np.linalg.norm(Tref[:3, 3]), 1e-9) + 1e-12
+
+
+@pytest.mark.parametrize("W,H,D,kw", SGBM_CASES + [(400, 100, 256, {}), (1241, 376, 128, {})])
+def test_sgbm_bit_exact(W, H, D, kw):
+    cam, args = _cam(W, H, D, **kw)
+    L, R = occluded_pair(W, H, d=min(24, D // 2))
+    got = cam.stereoSGBM.compute(L, R)
+    assert got.dtype == np.int16 and np.array_equal(got, O.sgbm_compute(L, R, args["sgbm_params"]))
+
+
+def test_sgbm_batch_and_idempotence():
+    W, H, D = 320, 96, 64
+    cam, args = _cam(W, H, D)
+    eng = cam.engine(max_batch=3)
+    L, R = occluded_pair(W, H)
+    Ls = np.stack([np.roll(L, 5 * i, 1) for i in range(3)])
+    Rs = np.stack([np.roll(R, 5 * i, 1) for i in range(3)])
+    a = eng.sgbm(eng.upload(Ls, "l"), eng.upload(Rs, "r")).cpu().numpy()
+    b = eng.sgbm(eng.upload(Ls, "l"), eng.upload(Rs, "r")).cpu().numpy()
+    assert np.array_equal(a, b)
+    for f in range(3):
+        assert np.array_equal(a[f], O.sgbm_compute(Ls[f], Rs[f], args["sgbm_params"]))
+
+
+def test_sgbm_properties_full_size():
+    # size-independent properties at the KITTI shape: first D columns invalid, constant-shift scene recovers its shift
+    W, H, D = 1241, 376, 128
+    cam, _ = _cam(W, H, D)
+    L, R = synth.kat_pair(W, H, d=24)
+    d = cam.stereoSGBM.compute(L, R)
+    assert (d[:, :D] == -16).all()
+    valid = d[d >= 0]
+    assert valid.size > 0.85 * (W - D) * H and np.median(valid) == 24 * 16
+
+
+def test_sgbm_rejects_bad_input():
+    cam, _ = _cam(320, 96, 64)
+    L, R = occluded_pair(320, 96)
+    with pytest.raises(ValueError):
+        cam.stereoSGBM.compute(L, R[:, :-1])
+    with pytest.raises(ValueError):
+        cam.stereoSGBM.compute(L.astype(np.float32), R)
+
+
+@pytest.mark.parametrize("W,H,n,usemask", [(640, 200, 500, False), (415, 333, 300, True), (1241, 376, 2000, True),
+                                           (1241, 376, 1000, False)])
+def test_orb_bit_exact(W, H, n, usemask):
+    cam, _ = _cam(W, H, 16)
+    od = StereoOdometer(cam, nfeatures=n, preprocessed_frames=True)
+    eng = od._engine()
+    L, _r = synth.kat_pair(W, H)
+    img = np.ascontiguousarray(L[:eng.ch, :eng.cw])
+    mask = block_mask(eng.ch, eng.cw) if usemask else None
+    kps, desc = od.orb.detectAndCompute(img, mask)
+    rk, rd = O.orb_detect_compute(img, mask, n)
+    got = np.array([[k.pt[0], k.pt[1], k.size, k.angle, k.response, k.octave] for k in kps], np.float32).reshape(-1, 6)
+    assert np.array_equal(got, rk) and np.array_equal(desc, rd)
+    assert all(k.class_id == -1 for k in kps)
+
+
+def test_orb_empty_and_ragged():
+    cam, _ = _cam(320, 120, 16)
+    od = StereoOdometer(cam, nfeatures=300, preprocessed_frames=True)
+    eng = od._engine()
+    flat = np.full((eng.ch, eng.cw), 77, np.uint8)
+    assert od.orb.detectAndCompute(flat, None) == ((), None)
+    L, _r = synth.kat_pair(320, 120)
+    img = np.ascontiguousarray(L[:eng.ch, :eng.cw])
+    zero_mask = np.zeros_like(img)
+    assert od.orb.detectAndCompute(img, zero_mask) == ((), None)
+    with pytest.raises(ValueError):
+        od.orb.detectAndCompute(img[:, :-3], None)
+
+
+@pytest.mark.parametrize("nq,nt", [(1, 2), (5, 2), (300, 257), (2000, 2000), (1798, 1801)])
+def test_knn_bit_exact_with_ties(nq, nt):
+    cam, _ = _cam(640, 200, 16)
+    od = StereoOdometer(cam, nfeatures=max(nq, nt), preprocessed_frames=True)
+    rng = np.random.default_rng(3)
+    q = rng.integers(0, 256, (nq, 32), dtype=np.uint8) & 0xF0
+    t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+    t[nt // 2:] &= 0xF0
+    ref = O.knn2_hamming(q, t)
+    mm = od.matcher.knnMatch(q, t, k=2)
+    got = np.array([[m[0].trainIdx, int(m[0].distance), m[1].trainIdx, int(m[1].distance)] for m in mm], np.int32)
+    assert np.array_equal(got, ref)
+    assert all(m[0].queryIdx == i and m[0].imgIdx == 0 for i, m in enumerate(mm))
+
+
+def test_compute_3d_matches_reference_contract():
+    W, H, D = 480, 160, 64
+    cam, args = _cam(W, H, D)
+    Ls, Rs, _ = synth.make_sequence(W, H, 1)
+    xyz, disp, img = cam.compute_3d(Ls[0], Rs[0], preprocessed=True)
+    port = O.StereoCameraPort(**args, backend="restated")
+    rxyz, rdisp, rimg = port.compute_3d(Ls[0], Rs[0], preprocessed=True)
+    assert xyz.dtype == np.float32 and disp.dtype == np.float32 and img.dtype == np.uint8
+    assert np.array_equal(disp, rdisp) and np.array_equal(img, rimg)
+    assert np.array_equal(xyz.view(np.uint32), rxyz.view(np.uint32))
+
+
+def _replay(g, **kw):
+    W, H, D, n = int(g["W"]), int(g["H"]), int(g["D"]), int(g["nfeatures"])
+    cam, _ = _cam(W, H, D)
+    assert tuple(cam.valid_region_left) == tuple(int(v) for v in g["roi"])
+    od = StereoOdometer(cam, nfeatures=n, preprocessed_frames=True, **kw)
+    for i in range(len(g["left"])):
+        ok = od.update(g["left"][i], g["right"][i])
+        assert ok == bool(g["ok_%d" % i]), i
+        assert od.skip_cause == str(g["cause_%d" % i]), i
+        assert od.skipped_frames == int(g["skipped_%d" % i]), i
+        if od.current_disparity is not None:
+            assert np.array_equal(np.rint(od.current_disparity * 16).astype(np.int16), g["disp16_%d" % i]), i
+            got = np.array([[k.pt[0], k.pt[1], k.size, k.angle, k.response, k.octave] for k in od.current_kps], np.float32)
+            assert np.array_equal(got.reshape(-1, 6), g["kp_%d" % i]) and np.array_equal(od.current_desc, g["desc_%d" % i]), i
+        assert _pose_close(od.c_T_w, g["cTw_%d" % i]), i
+        assert _pose_close(od.current_pose(), g["pose_%d" % i]), i
+    return od
+
+
+@pytest.mark.parametrize("name,kw", [("seq_small", {}), ("seq_skip", {}),
+                                     ("seq_filters", dict(rigidity_threshold=0.06, outlier_threshold=0.02))])
+def test_update_reproduces_reference_fixtures(golden, name, kw):
+    _replay(golden(name), **kw)
+
+
+def test_seam_fixture(golden):
+    g = golden("seams_small")
+    H, W = g["left"].shape
+    cam, _ = _cam(W, H, 64)
+    assert np.array_equal(cam.stereoSGBM.compute(g["left"], g["right"]), g["sgbm"])
+
+
+def test_update_vs_oracle_kitti_shape():
+    W, H, D, n = 1241, 376, 128, 2000
+    Ls, Rs, _ = synth.make_sequence(W, H, 3)
+    cam, args = _cam(W, H, D)
+    od = StereoOdometer(cam, nfeatures=n, preprocessed_frames=True)
+    po = O.StereoOdometerPort(O.StereoCameraPort(**args, backend="cv2"), nfeatures=n, preprocessed_frames=True)
+    for i in range(3):
+        assert od.update(Ls[i], Rs[i]) == po.update(Ls[i], Rs[i])
+        assert np.array_equal(od.current_disparity, po.cur[1])
+        assert np.array_equal(od._host(od._cur, "kp_array"), po.cur[3]) and np.array_equal(od.current_desc, po.cur[4])
+        if i:
+            eng = od._engine()
+            assert np.array_equal(eng.matches[:od.last_match_count].cpu().numpy(), po.last_matches)
+        assert _pose_close(od.c_T_w, po.c_T_w)
+    # lazily materialised reference-typed state
+    assert od.current_3d.shape == (od._engine().ch, od._engine().cw, 3)
+    assert np.array_equal(od.current_3d.view(np.uint32), po.cur[2].view(np.uint32))
+    assert od.prev_img is not None and od.current_img.dtype == np.uint8
