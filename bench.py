@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py — stereo frames/sec of the openVO per-frame hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path on the host cores
+
+A "step" advances S independent KITTI-shaped synthetic stereo sequences by one frame each on every GPU (BatchOdometer:
+SGBM 128 disp + ORB 2000 kp + Hamming 2-NN/ratio + fused 3-D lookup + Umeyama + the reference's skip state machine), so a
+step is S frames per GPU (weak scaling: S per GPU is fixed).  `value` is measured with the frames already resident in
+HBM; `e2e` is the same loop through the public host-buffer API (numpy frames in pinned memory -> H2D every step, poses
+read back every step).  Timing: CUDA events around the K steps, barrier + synchronize on both sides, max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    "K": dict(W=1241, H=376, D=128, n=2000, name="KITTI-shaped 1241x376 stereo, ORB 2000 kp, StereoSGBM 128 disp"),
+    "F": dict(W=1920, H=1080, D=256, n=5000, name="1920x1080 stereo, ORB 5000 kp, StereoSGBM 256 disp"),
+    "S": dict(W=640, H=200, D=64, n=500, name="small 640x200 stereo, ORB 500 kp, StereoSGBM 64 disp (dev only)"),
+}
+N_DISTINCT = 6  # distinct rendered frames; sequences ping-pong through them with different phases
+
+
+def frame_index(step, seq):
+    period = 2 * (N_DISTINCT - 1)
+    k = (step + seq) % period
+    return k if k < N_DISTINCT else period - k
+
+
+def make_frames(cfg):
+    from openvo_b200 import synth
+    cache = os.path.join(tempfile.gettempdir(), "ovo_bench_%dx%d_%d.npz" % (cfg["W"], cfg["H"], N_DISTINCT))
+    if os.path.exists(cache):
+        z = np.load(cache)
+        return z["L"], z["R"]
+    L, R, _ = synth.make_sequence(cfg["W"], cfg["H"], N_DISTINCT)
+    try:
+        np.savez(cache, L=L, R=R)
+    except Exception:
+        pass
+    return L, R
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port with the cv2 back end (what a user of the reference runs), one process per host core
+# ---------------------------------------------------------------------------------------------------------------------------
+def cpu_worker(cfg_key, frames_file, seq, warmup, steps):
+    import cv2
+    from openvo_b200 import synth
+    from oracle import openvo_port as O
+    cv2.setNumThreads(1)
+    cfg = CONFIGS[cfg_key]
+    z = np.load(frames_file)
+    L, R = z["L"], z["R"]
+    args = synth.camera_args(cfg["W"], cfg["H"], cfg["D"])
+    od = O.StereoOdometerPort(O.StereoCameraPort(**args, backend="cv2"), nfeatures=cfg["n"], preprocessed_frames=True)
+    for s in range(warmup):
+        od.update(L[frame_index(s, seq)], R[frame_index(s, seq)])
+    sys.stdout.write("READY\n")
+    sys.stdout.flush()
+    sys.stdin.readline()  # start gun
+    t0 = time.time()
+    for s in range(warmup, warmup + steps):
+        od.update(L[frame_index(s, seq)], R[frame_index(s, seq)])
+    sys.stdout.write("DONE %.6f\n" % (time.time() - t0))
+    sys.stdout.flush()
+
+
+def run_cpu(cfg_key, L, R, warmup, steps, nprocs):
+    """-> (frames/s aggregate, wall seconds).  All processes start their timed frames together."""
+    with tempfile.NamedTemporaryFile(suffix=".npz", delete=False) as fh:
+        np.savez(fh, L=L, R=R)
+        frames_file = fh.name
+    env = dict(os.environ, OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1")
+    procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--_cpu_worker", cfg_key, frames_file, str(i), str(warmup),
+                               str(steps)], stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True, env=env) for i in range(nprocs)]
+    for p in procs:
+        assert p.stdout.readline().strip() == "READY"
+    t0 = time.time()
+    for p in procs:
+        p.stdin.write("go\n")
+        p.stdin.flush()
+    for p in procs:
+        line = p.stdout.readline()
+        assert line.startswith("DONE"), line
+    wall = time.time() - t0
+    for p in procs:
+        p.wait()
+    os.unlink(frames_file)
+    return nprocs * steps / wall, wall
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def result(self):
+        self.stop_flag = True
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def algorithmic_bytes(tag, eng, nb):
+    """ALGORITHMIC HBM bytes of one launch of the named kernel (DESIGN.md 'Kernels'); V = one frame's cost volume."""
+    D = eng.cfg.sgbm.numDisparities
+    Dp = 64 if D <= 64 else (128 if D <= 128 else 256)
+    W, H = eng.W, eng.H
+    V = H * (W - D) * Dp * 2
+    table = {
+        "k_sgbm_prep": 2 * W * H + 16 * W * H,
+        "k_sgbm_cost_t": 16 * W * H + V,
+        "k_sgbm_vert_t": V + 3 * V,
+        "k_sgbm_horiz_t": V + 3 * V + 2 * W * H,
+        "k_sgbm_paths_t": V + 2 * W * H,
+    }
+    return table.get(tag, 0) * nb
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="K", choices=list(CONFIGS))
+    ap.add_argument("--seqs", type=int, default=8, help="independent sequences (= frames per step) per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--_cpu_worker", nargs=5, default=None)
+    a = ap.parse_args()
+    if a._cpu_worker:
+        k, f, seq, wu, st = a._cpu_worker
+        return cpu_worker(k, f, int(seq), int(wu), int(st))
+    cfg = CONFIGS[a.config]
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
+    workload = "synthetic %s, %d independent sequences per GPU, 1 frame each per step" % (cfg["name"], a.seqs)
+    metric, unit = "stereo frames/sec", "frames/s"
+
+    L, R = make_frames(cfg)
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        cores = host_cores()
+        fps, wall = run_cpu(a.config, L, R, max(a.warmup, 1), a.steps, cores)
+        sample = "%d processes x %d frames each (cv2.setNumThreads(1)), wall %.1f s" % (cores, a.steps, wall)
+        line = {"impl": "reference", "metric": metric, "value": fps, "unit": unit, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": 1e3 * wall / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i16",
+                "data": "synthetic", "config": {"workload": "synthetic %s, one sequence per host core, 1 frame each per step" % cfg["name"],
+                                                "frames_per_step": cores},
+                "cpu_baseline": {"value": fps, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": fps, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ---- CPU baseline first (before CUDA is initialised in this process), rank 0 at N=1 only
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cores = host_cores()
+        nfr = 24 if a.config != "F" else 4
+        fps, wall = run_cpu(a.config, L, R, 2, nfr, cores)
+        cpu_baseline = {"value": fps, "unit": unit, "cores": cores, "kind": "port",
+                        "sample": "oracle port on cv2 (the reference's CPU path): %d processes x %d frames (cv2 threads=1 each), "
+                                  "wall %.1f s" % (cores, nfr, wall)}
+
+    import torch
+    import torch.distributed as dist
+    from openvo_b200 import StereoCamera, synth, _native
+    from openvo_b200.batch import BatchOdometer
+    from openvo_b200 import dist as odist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+    S = a.seqs
+    cam = StereoCamera(**synth.camera_args(cfg["W"], cfg["H"], cfg["D"]))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def fresh():
+        return BatchOdometer(cam, S, nfeatures=cfg["n"], preprocessed_frames=True)
+
+    dev_L, dev_R = torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()
+    lib = _native.load()
+
+    def run(bo, steps, first_step, host):
+        ok = 0
+        for s in range(first_step, first_step + steps):
+            idx = [frame_index(s, rank * S + q) for q in range(S)]
+            if host:
+                res = bo.update(L[idx], R[idx])
+            else:
+                ti = torch.tensor(idx, device="cuda")
+                res = bo.update_device(dev_L[ti], dev_R[ti])
+            ok += sum(res)
+        return ok
+
+    def timed(host):
+        bo = fresh()
+        run(bo, warmup, 0, host)
+        eng = bo.engine
+        h2d0, d2h0, l0 = eng.h2d_bytes, eng.d2h_bytes, lib.ovo_launch_count()
+        sampler = ClockSampler(local_rank)
+        barrier()
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ok = run(bo, a.steps, warmup, host)
+        if world > 1:  # the only exchange: per-frame relative transforms + status, once per chunk
+            T = np.stack([od.last_T if od.last_T is not None else np.eye(4) for od in bo.odometers])[:, None]
+            st = np.ones((S, 1), np.int32)
+            odist.gather_poses(T, st, odist.shard_sequences(S * world, rank, world), S * world)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.result()
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return dict(ms=ms, ok=ok, h2d=(eng.h2d_bytes - h2d0) / a.steps, d2h=(eng.d2h_bytes - d2h0) / a.steps,
+                    launches=lib.ovo_launch_count() - l0, clocks=clocks, bo=bo)
+
+    dev = timed(host=False)
+    e2e = timed(host=True)
+    frames = S * world * a.steps
+    value = frames / (dev["ms"] * 1e-3)
+    e2e_value = frames / (e2e["ms"] * 1e-3)
+
+    # ---- roofline leg: per-kernel CUDA-event durations over an identical region (events on the launching stream)
+    roofline, per_kernel = None, {}
+    if rank == 0:
+        bo = dev["bo"]
+        lib.ovo_profile_enable(1)
+        run(bo, min(a.steps, 5), warmup + a.steps, False)
+        prof = _native.profile_read(lib)
+        lib.ovo_profile_enable(0)
+        tot = sum(v[0] for v in prof.values()) or 1.0
+        per_kernel = {k: {"ms_per_launch": v[0] / v[1], "launches": v[1], "share": v[0] / tot} for k, v in prof.items()}
+        top = max(prof, key=lambda k: prof[k][0])
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak, which = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+        abytes = algorithmic_bytes(top, bo.engine, S)
+        dur_s = prof[top][0] / prof[top][1] * 1e-3
+        achieved = abytes / dur_s / 1e9 if dur_s > 0 else 0.0
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(a.config, {}).get(top)
+        except Exception:
+            pass
+        roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": which, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": abytes,
+                    "ms_per_launch": dur_s * 1e3, "share_of_step": prof[top][0] / tot}
+    if rank == 0:
+        line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": a.steps, "warmup": warmup,
+                "ms_per_step": dev["ms"] / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i16",
+                "data": "synthetic",
+                "config": {"workload": workload, "frames_per_step": S * world, "sequences_per_gpu": S, "distinct_frames": N_DISTINCT,
+                           "l2_policy": "inputs+working set larger than L2: %d frames x ~0.55 GB SGBM volumes per step" % S,
+                           "frames_committed": dev["ok"]},
+                "clocks": dev["clocks"], "gpu_launches": dev["launches"],
+                "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                        "ms_per_step": e2e["ms"] / a.steps},
+                "roofline": roofline, "kernels": per_kernel}
+        if cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

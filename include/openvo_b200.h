@@ -105,6 +105,16 @@ int ovo_match_points(ovo_ctx* ctx, const int32_t* nn_dev, int nq, double match_t
 int ovo_rigid_transform(ovo_ctx* ctx, const float* pts1_dev, const float* pts2_dev, const int32_t* count_dev, int cap,
                         double* out_dev, void* stream);
 
+/* Instrumentation for bench.py: number of kernels launched by this library so far; optional per-kernel CUDA-event timing
+ * (events recorded on the launching stream around every kernel while enabled).  ovo_profile_read synchronises the device
+ * and returns, per kernel name ('\n'-separated in `names`), the summed milliseconds and the launch count since the last
+ * read. */
+long long ovo_launch_count(void);
+/* bytes this context has moved between host and device itself (the keypoint-selection staging of ovo_orb_detect_compute) */
+void ovo_transfer_bytes(ovo_ctx* ctx, long long* h2d, long long* d2h);
+void ovo_profile_enable(int on);
+int ovo_profile_read(char* names, int names_len, float* total_ms, int* counts, int max_entries);
+
 #ifdef __cplusplus
 }
 #endif

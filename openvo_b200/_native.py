@@ -46,6 +46,10 @@ _SIGNATURES = {
     "ovo_knn2_hamming": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),
     "ovo_match_points": (_i, [_vp, _vp, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ovo_rigid_transform": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "ovo_launch_count": (ctypes.c_longlong, []),
+    "ovo_transfer_bytes": (None, [_vp, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong)]),
+    "ovo_profile_enable": (None, [_i]),
+    "ovo_profile_read": (_i, [ctypes.c_char_p, _i, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_i), _i]),
 }
 EXPORTS = tuple(_SIGNATURES)
 
@@ -100,3 +104,13 @@ def ptr(x):
     if hasattr(x, "data_ptr"):
         return x.data_ptr()
     return x.ctypes.data
+
+
+def profile_read(lib):
+    """-> {kernel name: (total ms, launches)} since the last read."""
+    names = ctypes.create_string_buffer(8192)
+    ms = (ctypes.c_float * 128)()
+    cnt = (ctypes.c_int * 128)()
+    n = lib.ovo_profile_read(names, 8192, ms, cnt, 128)
+    tags = names.value.decode().split("\n")[:n]
+    return {t: (float(ms[i]), int(cnt[i])) for i, t in enumerate(tags)}

@@ -1,0 +1,44 @@
+"""BatchOdometer — S independent stereo sequences advanced one frame each per call (BASELINE.json config 5, and the
+throughput path of bench.py).  Per-sequence semantics are exactly StereoOdometer.update's (the same state machine object
+is used); only the device work is batched: one SGBM / ORB launch set over all S frames (grid.z = frame), S pair steps
+queued back to back, a single 144*S-byte read-back and one stream synchronisation per call.
+"""
+import numpy as np
+
+from .stereo_odometer import StereoOdometer
+
+
+class BatchOdometer:
+    def __init__(self, stereo_camera, n_sequences, nfeatures=500, **kw):
+        self.n = int(n_sequences)
+        self.stereo = stereo_camera
+        self.odometers = [StereoOdometer(stereo_camera, nfeatures=nfeatures, _max_batch=self.n, **kw) for _ in range(self.n)]
+        self.engine = self.odometers[0]._engine()
+
+    def update(self, lefts, rights):
+        """lefts/rights: numpy uint8 [S,H,W] host frames (rectified, gray) -> list of S bools."""
+        eng = self.engine
+        return self.update_device(eng.upload(np.asarray(lefts), "b_l"), eng.upload(np.asarray(rights), "b_r"))
+
+    def update_device(self, lefts, rights):
+        """Same, with the frames already resident on the device (torch uint8 [S,H,W])."""
+        eng = self.engine
+        frames = eng.frames(lefts, rights)
+        queued = []
+        for i, (od, fr) in enumerate(zip(self.odometers, frames)):
+            if od._cur is not None and fr.n_kp >= od.min_matches and fr.n_kp >= 2:
+                eng.pair_async(od._cur, fr, od.match_threshold, slot=i)
+                queued.append(i)
+        res = eng.pair_collect(self.n) if queued else []
+        out = []
+        for i, (od, fr) in enumerate(zip(self.odometers, frames)):
+            out.append(od._advance(fr, first=(i, res[i]) if i in queued else None))
+        return out
+
+    def poses(self):
+        return np.stack([od.current_pose() for od in self.odometers])
+
+    def relative_transforms(self):
+        """Last committed relative transform per sequence (identity when the last frame was skipped) and status words."""
+        T = np.stack([od.last_T if od.last_T is not None else np.eye(4) for od in self.odometers])
+        return T

@@ -1,6 +1,10 @@
 // C ABI of openvo_b200 (include/openvo_b200.h): context, workspace carving and the per-seam entry points.
+#include <atomic>
 #include <cstdarg>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -16,6 +20,33 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+
+// ---- launch counter + optional per-kernel CUDA-event profile (bench.py's roofline leg) -----------------------------------
+#ifndef OVO_EMU
+namespace {
+struct ProfEntry { const char* tag; cudaEvent_t a, b; };
+std::atomic<long long> g_launches{0};
+bool g_prof_on = false;
+std::vector<ProfEntry> g_prof;
+std::mutex g_prof_mu;
+}  // namespace
+void prof_pre(const char* tag, cudaStream_t st) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    ProfEntry e;
+    e.tag = tag;
+    cudaEventCreate(&e.a);
+    cudaEventCreate(&e.b);
+    cudaEventRecord(e.a, st);
+    g_prof.push_back(e);
+}
+void prof_post(cudaStream_t st) {
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (!g_prof.empty()) cudaEventRecord(g_prof.back().b, st);
+}
+#endif
 
 // defined in orb.cu / match.cu
 void orb_make_resize_tables(const OrbDims& d, int32_t* tab, int* tab_off, int* total);
@@ -97,12 +128,64 @@ struct ovo_ctx {
     float* h_resp;     // [max_batch][cand_cap][2]
     int32_t* h_sel;    // [max_batch][kp_cap]
     int32_t* h_nsel;   // [max_batch]
+    long long h2d_bytes = 0, d2h_bytes = 0;  // staging traffic of the keypoint selection
 };
 
 extern "C" {
 
 const char* ovo_last_error(void) { return g_err; }
 int ovo_abi_version(void) { return OVO_ABI_VERSION; }
+
+void ovo_transfer_bytes(ovo_ctx* c, long long* h2d, long long* d2h) {
+    *h2d = c ? c->h2d_bytes : 0;
+    *d2h = c ? c->d2h_bytes : 0;
+}
+
+long long ovo_launch_count(void) {
+#ifndef OVO_EMU
+    return g_launches.load();
+#else
+    return 0;
+#endif
+}
+
+void ovo_profile_enable(int on) {
+#ifndef OVO_EMU
+    g_prof_on = on != 0;
+#endif
+}
+
+int ovo_profile_read(char* names, int names_len, float* total_ms, int* counts, int max_entries) {
+#ifndef OVO_EMU
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    std::map<std::string, std::pair<double, int>> acc;
+    std::vector<std::string> order;
+    for (auto& e : g_prof) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e.a, e.b);
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+        if (!acc.count(e.tag)) order.push_back(e.tag);
+        acc[e.tag].first += ms;
+        acc[e.tag].second += 1;
+    }
+    g_prof.clear();
+    std::string joined;
+    int n = 0;
+    for (auto& t : order) {
+        if (n >= max_entries) break;
+        total_ms[n] = (float)acc[t].first;
+        counts[n] = acc[t].second;
+        joined += t + "\n";
+        n++;
+    }
+    snprintf(names, names_len, "%s", joined.c_str());
+    return n;
+#else
+    return 0;
+#endif
+}
 
 int ovo_cropped_size(const ovo_config* cfg, int* cw, int* ch) {
     Layout L;
@@ -200,9 +283,11 @@ int ovo_orb_detect_compute(ovo_ctx* c, const uint8_t* img, const uint8_t* mask, 
     for (int f = 0; f < nb; f++)
         OVO_CUDA(cudaMemcpyAsync(c->h_lvl + 32 * f, (uint8_t*)c->orb0.lvl_count + L.frame_bytes * f, 17 * 4, cudaMemcpyDeviceToHost, st));
     OVO_CUDA(cudaStreamSynchronize(st));
+    c->d2h_bytes += 17 * 4 * (long long)nb;
     for (int f = 0; f < nb; f++) {
         const int total = c->h_lvl[32 * f + 16];
         if (total > d.cand_cap) { set_error("ORB candidate overflow (%d > %d)", total, d.cand_cap); return 1; }
+        c->d2h_bytes += (long long)total * 8;
         if (total > 0)
             OVO_CUDA(cudaMemcpyAsync(c->h_resp + (size_t)f * d.cand_cap * 2, (uint8_t*)c->orb0.cand_resp + L.frame_bytes * f,
                                      (size_t)total * 8, cudaMemcpyDeviceToHost, st));
@@ -225,6 +310,7 @@ int ovo_orb_detect_compute(ovo_ctx* c, const uint8_t* img, const uint8_t* mask, 
         if (c->h_nsel[f] < 0) { set_error("ORB keypoint capacity exceeded (ties at the retainBest boundary)"); return 1; }
         n_kp_host[f] = c->h_nsel[f];
         max_sel = c->h_nsel[f] > max_sel ? c->h_nsel[f] : max_sel;
+        c->h2d_bytes += (long long)c->h_nsel[f] * 4 + 4;
         if (c->h_nsel[f] > 0)
             OVO_CUDA(cudaMemcpyAsync((uint8_t*)c->orb0.sel + L.frame_bytes * f, c->h_sel + (size_t)f * d.kp_cap, (size_t)c->h_nsel[f] * 4,
                                      cudaMemcpyHostToDevice, st));

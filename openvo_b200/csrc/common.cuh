@@ -7,7 +7,16 @@
 #define OVO_DYN_SMEM(type, name)                                  \
     extern __shared__ __align__(16) unsigned char name##_raw[]; \
     type* name = reinterpret_cast<type*>(name##_raw)
-#define OVO_LAUNCH(kern, grid, block, smem, st, ...) kern<<<grid, block, smem, st>>>(__VA_ARGS__)
+namespace ovo {
+void prof_pre(const char* tag, cudaStream_t st);   // counts the launch; records a start event when profiling is on
+void prof_post(cudaStream_t st);
+}
+#define OVO_LAUNCH(kern, grid, block, smem, st, ...)          \
+    do {                                                      \
+        ovo::prof_pre(#kern, st);                             \
+        kern<<<grid, block, smem, st>>>(__VA_ARGS__);         \
+        ovo::prof_post(st);                                   \
+    } while (0)
 #endif
 #include <cstdint>
 #include <cstddef>

@@ -537,11 +537,11 @@ __global__ void k_ccl_apply(const int16_t* __restrict__ img, const int32_t* __re
 template <int NPR>
 int launch_paths(const SgbmDims& d, const SgbmWorkspace& ws, size_t ws_stride, int nb, cudaStream_t st) {
     dim3 gv(cdiv(d.W1, 8), 3, nb);
-    { auto kern = k_sgbm_vert<NPR>; OVO_LAUNCH(kern, gv, dim3(256), 0, st, d, ws, ws_stride); }
+    { auto k_sgbm_vert_t = k_sgbm_vert<NPR>; OVO_LAUNCH(k_sgbm_vert_t, gv, dim3(256), 0, st, d, ws, ws_stride); }
     OVO_LAUNCH_CHECK();
     dim3 gh(d.H, nb);
     const size_t smem = (size_t)d.W * 4 + (size_t)d.W * 2 + 16;
-    { auto kern = k_sgbm_horiz<NPR>; OVO_LAUNCH(kern, gh, dim3(64), smem, st, d, ws, ws_stride); }
+    { auto k_sgbm_horiz_t = k_sgbm_horiz<NPR>; OVO_LAUNCH(k_sgbm_horiz_t, gh, dim3(64), smem, st, d, ws, ws_stride); }
     OVO_LAUNCH_CHECK();
     return 0;
 }
@@ -551,7 +551,7 @@ int launch_cost(const SgbmDims& d, const SgbmWorkspace& ws, size_t ws_stride, in
     const int npairs = d.Dp / 2, upb = kCostThreads / npairs;
     const int units = cdiv(d.W1, TX) * cdiv(d.H, kCostRS);
     dim3 grid(cdiv(units, upb), 1, nb), block(npairs, upb);
-    { auto kern = k_sgbm_cost<SW2, TX>; OVO_LAUNCH(kern, grid, block, 0, st, d, ws, ws_stride); }
+    { auto k_sgbm_cost_t = k_sgbm_cost<SW2, TX>; OVO_LAUNCH(k_sgbm_cost_t, grid, block, 0, st, d, ws, ws_stride); }
     OVO_LAUNCH_CHECK();
     return 0;
 }

@@ -43,13 +43,16 @@ class Engine:
         if not self.ctx:
             raise N.NativeError(self.lib.ovo_last_error().decode())
         self._pin = {}
-        # small persistent buffers of the pair step
-        self.nn = torch.empty((self.kp_cap, 4), dtype=torch.int32, device=self.device)
-        self.matches = torch.empty((self.kp_cap, 3), dtype=torch.int32, device=self.device)
-        self.pts1 = torch.empty((self.kp_cap, 3), dtype=torch.float32, device=self.device)
-        self.pts2 = torch.empty((self.kp_cap, 3), dtype=torch.float32, device=self.device)
-        self.pair_out = torch.empty(18, dtype=torch.float64, device=self.device)  # [0:16] rigid, [16:18] counts (as i32 view)
-        self.pair_host = torch.empty(18, dtype=torch.float64).pin_memory()
+        # persistent buffers of the pair step, one slot per frame of the batch
+        nb = self.max_batch
+        self.nn = torch.empty((nb, self.kp_cap, 4), dtype=torch.int32, device=self.device)
+        self.matches = torch.empty((nb, self.kp_cap, 3), dtype=torch.int32, device=self.device)
+        self.pts1 = torch.empty((nb, self.kp_cap, 3), dtype=torch.float32, device=self.device)
+        self.pts2 = torch.empty((nb, self.kp_cap, 3), dtype=torch.float32, device=self.device)
+        self.pair_out = torch.zeros((nb, 18), dtype=torch.float64, device=self.device)  # [0:16] rigid, [16] two i32 counts
+        self.pair_host = torch.zeros((nb, 18), dtype=torch.float64).pin_memory()
+        self._d2h = 0
+        self._h2d = 0
 
     def __del__(self):
         try:
@@ -58,6 +61,20 @@ class Engine:
                 self.ctx = None
         except Exception:
             pass
+
+    def _lib_bytes(self):
+        h, d = ctypes.c_longlong(), ctypes.c_longlong()
+        self.lib.ovo_transfer_bytes(self.ctx, ctypes.byref(h), ctypes.byref(d))
+        return h.value, d.value
+
+    @property
+    def h2d_bytes(self):
+        """host->device bytes moved so far (frame uploads + the library's own staging)."""
+        return self._h2d + self._lib_bytes()[0]
+
+    @property
+    def d2h_bytes(self):
+        return self._d2h + self._lib_bytes()[1]
 
     # ---- helpers ---------------------------------------------------------------------------------------------------
     def _stream(self):
@@ -75,6 +92,7 @@ class Engine:
         a = np.ascontiguousarray(arr)
         stage = self._pinned(key, a.shape, torch.uint8)
         stage.numpy()[...] = a
+        self._h2d += a.nbytes
         return stage.to(self.device, non_blocking=True)
 
     # ---- seams -------------------------------------------------------------------------------------------------------
@@ -115,25 +133,39 @@ class Engine:
         return kp, desc, list(n)
 
     def knn2(self, desc_q, nq, desc_t, nt, out=None):
-        nn = self.nn if out is None else out
+        nn = self.nn[0] if out is None else out
         N.check(self.lib, self.lib.ovo_knn2_hamming(self.ctx, desc_q.data_ptr(), nq, desc_t.data_ptr(), nt, nn.data_ptr(), self._stream()))
         return nn
 
-    def pair(self, a, b, match_threshold):
-        """Frames a (query) and b (train): 2-NN + ratio + fused 3-D lookup + rigid alignment, all on the device, one
-        D2H of 144 bytes.  Returns (n_matches, n_bad_lookups, out16 numpy)."""
-        self.knn2(a.desc, a.n_kp, b.desc, b.n_kp)
-        counts_ptr = self.pair_out.data_ptr() + 16 * 8
-        N.check(self.lib, self.lib.ovo_match_points(self.ctx, self.nn.data_ptr(), a.n_kp, float(match_threshold), a.kp.data_ptr(),
-                                                    b.kp.data_ptr(), a.disp.data_ptr(), b.disp.data_ptr(), self.matches.data_ptr(),
-                                                    self.pts1.data_ptr(), self.pts2.data_ptr(), counts_ptr, self._stream()))
-        N.check(self.lib, self.lib.ovo_rigid_transform(self.ctx, self.pts1.data_ptr(), self.pts2.data_ptr(), counts_ptr, self.kp_cap,
-                                                       self.pair_out.data_ptr(), self._stream()))
-        self.pair_host.copy_(self.pair_out, non_blocking=True)
+    def pair_async(self, a, b, match_threshold, slot=0):
+        """Frames a (query) and b (train): 2-NN + ratio + fused 3-D lookup + rigid alignment, all on the device; results
+        land in pair_out[slot].  Nothing is read back until pair_collect()."""
+        st = self._stream()
+        nn, out = self.nn[slot], self.pair_out[slot]
+        N.check(self.lib, self.lib.ovo_knn2_hamming(self.ctx, a.desc.data_ptr(), a.n_kp, b.desc.data_ptr(), b.n_kp, nn.data_ptr(), st))
+        counts_ptr = out.data_ptr() + 16 * 8
+        N.check(self.lib, self.lib.ovo_match_points(self.ctx, nn.data_ptr(), a.n_kp, float(match_threshold), a.kp.data_ptr(),
+                                                    b.kp.data_ptr(), a.disp.data_ptr(), b.disp.data_ptr(),
+                                                    self.matches[slot].data_ptr(), self.pts1[slot].data_ptr(),
+                                                    self.pts2[slot].data_ptr(), counts_ptr, st))
+        N.check(self.lib, self.lib.ovo_rigid_transform(self.ctx, self.pts1[slot].data_ptr(), self.pts2[slot].data_ptr(), counts_ptr,
+                                                       self.kp_cap, out.data_ptr(), st))
+
+    def pair_collect(self, nslots=1):
+        """One D2H (144 bytes per slot) + one stream sync -> list of (n_matches, n_bad_lookups, out16 numpy)."""
+        self.pair_host[:nslots].copy_(self.pair_out[:nslots], non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
+        self._d2h += nslots * 144
         host = self.pair_host.numpy()
-        counts = host[16:18].view(np.int32)
-        return int(counts[0]), int(counts[1]), host[:16].copy()
+        res = []
+        for s in range(nslots):
+            counts = host[s, 16:17].view(np.int32)
+            res.append((int(counts[0]), int(counts[1]), host[s, :16].copy()))
+        return res
+
+    def pair(self, a, b, match_threshold):
+        self.pair_async(a, b, match_threshold, 0)
+        return self.pair_collect(1)[0]
 
     def rigid(self, pts1, pts2):
         """numpy float32 [m,3] x2 -> out16 (estimateAffine3D seam for the optional filter paths)."""

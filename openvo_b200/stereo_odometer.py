@@ -78,9 +78,10 @@ class StereoOdometer:
     MAX_ROTATION_CHANGE = np.pi / 3
 
     def __init__(self, stereo_camera, nfeatures=500, match_threshold=0.8, rigidity_threshold=0, outlier_threshold=0,
-                 preprocessed_frames=False, min_matches=10):
+                 preprocessed_frames=False, min_matches=10, _max_batch=1):
         self.stereo = stereo_camera
         self._nfeatures = nfeatures
+        self._max_batch = _max_batch  # >1 only when driven by openvo_b200.batch.BatchOdometer
         self._cur = None   # last committed frame (device resident)
         self._prev = None  # the one before
         self.orb, self.matcher = _OrbHandle(self), _MatcherHandle(self)
@@ -92,9 +93,10 @@ class StereoOdometer:
         self.c_T_w_prev = np.eye(4)
         self.skip_cause = ""
         self.last_match_count = 0
+        self.last_T = None
 
     def _engine(self):
-        return self.stereo.engine(self._nfeatures, 1, float(self.MIN_VALID_DISPARITY), float(self.MAX_VALID_DISPARITY))
+        return self.stereo.engine(self._nfeatures, self._max_batch, float(self.MIN_VALID_DISPARITY), float(self.MAX_VALID_DISPARITY))
 
     # ---- lazily materialised public state (reference types) --------------------------------------------------------------
     def _host(self, frame, what):
@@ -164,6 +166,11 @@ class StereoOdometer:
         left, right = self.stereo._prepare(img_left, img_right, self.preprocessed_frames)
         eng = self._engine()
         frame = eng.frames(eng.upload(left[None], "upd_l"), eng.upload(right[None], "upd_r"))[0]
+        return self._advance(frame)
+
+    def _advance(self, frame, first=None):
+        """The state machine of ``update`` for an already extracted frame.  ``first`` optionally carries the device result
+        of the (current -> frame) pair step when a batch driver has already launched it."""
         if frame.n_kp < self.min_matches:
             self.skipped_frames += 1
             self.skip_cause = "keypoints"
@@ -171,7 +178,7 @@ class StereoOdometer:
         if self._cur is None:
             self.save_frame_update(frame)
             return True
-        T = self._relative(self._cur, frame)
+        T = self._relative(self._cur, frame, first)
         if T is not None:
             self.c_T_w_prev = self.c_T_w
             self.c_T_w = T @ self.c_T_w
@@ -186,15 +193,20 @@ class StereoOdometer:
             self.skipped_frames += 1
             return False
         self.skipped_frames = 0
+        self.last_T = T
         self.save_frame_update(frame)
         return True
 
-    def _relative(self, a, b):
+    def _relative(self, a, b, result=None):
         """point_clouds + point_cloud_transform for device frames a -> b."""
         eng = self._engine()
         if b.n_kp < 2:
             raise IndexError("tuple index out of range")  # the reference indexes m[1] (ref: stereo_odometer.py:164)
-        n, bad, out = eng.pair(a, b, self.match_threshold)
+        slot = 0
+        if result is None:
+            n, bad, out = eng.pair(a, b, self.match_threshold)
+        else:
+            slot, (n, bad, out) = result
         self.last_match_count = n
         if n < self.min_matches:
             self.skip_cause = "matches"
@@ -202,7 +214,7 @@ class StereoOdometer:
         if bad:
             raise ZeroDivisionError("division by zero")  # ref: stereo_odometer.py:79 with every tap skipped
         if self.rigidity_threshold > 0 or self.outlier_threshold > 0:
-            return self.point_cloud_transform(eng.pts1[:n].cpu().numpy(), eng.pts2[:n].cpu().numpy())
+            return self.point_cloud_transform(eng.pts1[slot, :n].cpu().numpy(), eng.pts2[slot, :n].cpu().numpy())
         if n < 10:
             self.skip_cause = "rigidity"
         return self._gate(out)

@@ -170,9 +170,34 @@ def test_update_vs_oracle_kitti_shape():
         assert np.array_equal(od._host(od._cur, "kp_array"), po.cur[3]) and np.array_equal(od.current_desc, po.cur[4])
         if i:
             eng = od._engine()
-            assert np.array_equal(eng.matches[:od.last_match_count].cpu().numpy(), po.last_matches)
+            assert np.array_equal(eng.matches[0, :od.last_match_count].cpu().numpy(), po.last_matches)
         assert _pose_close(od.c_T_w, po.c_T_w)
     # lazily materialised reference-typed state
     assert od.current_3d.shape == (od._engine().ch, od._engine().cw, 3)
     assert np.array_equal(od.current_3d.view(np.uint32), po.cur[2].view(np.uint32))
     assert od.prev_img is not None and od.current_img.dtype == np.uint8
+
+
+def test_batch_odometer_equals_single_stream(golden):
+    from openvo_b200.batch import BatchOdometer
+    g = golden("seq_skip")
+    W, H, D, n = int(g["W"]), int(g["H"]), int(g["D"]), int(g["nfeatures"])
+    cam, _ = _cam(W, H, D)
+    S = 3
+    bo = BatchOdometer(cam, S, nfeatures=n, preprocessed_frames=True)
+    nfr = len(g["left"])
+    # sequence s replays the fixture delayed by s frames (so the batch holds frames in different states)
+    for step in range(nfr + S - 1):
+        idx = [min(max(step - s, 0), nfr - 1) for s in range(S)]
+        bo.update(g["left"][idx], g["right"][idx])
+    singles = []
+    for s in range(S):
+        od = StereoOdometer(cam, nfeatures=n, preprocessed_frames=True)
+        for step in range(nfr + S - 1):
+            i = min(max(step - s, 0), nfr - 1)
+            od.update(g["left"][i], g["right"][i])
+        singles.append(od)
+    for s in range(S):
+        assert np.array_equal(bo.odometers[s].c_T_w, singles[s].c_T_w)
+        assert bo.odometers[s].skip_cause == singles[s].skip_cause
+        assert bo.odometers[s].skipped_frames == singles[s].skipped_frames
