@@ -491,33 +491,63 @@ __device__ __forceinline__ void ccl_union(int32_t* L, int a, int b) {
     } while (!done);
 }
 
-__global__ void k_ccl_init(const int16_t* __restrict__ img, int32_t* label, int32_t* csize, int n, size_t img_stride,
-                           size_t ws_stride) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x, f = blockIdx.y;
-    if (i >= n) return;
-    frame_ptr(label, ws_stride, f)[i] = frame_ptr(img, img_stride, f)[i] != kInv ? i : -1;
-    frame_ptr(csize, ws_stride, f)[i] = 0;
+// Speckle filter = connected components over 4-neighbour edges |a-b| <= maxDiff (order-independent, so any labelling
+// algorithm gives OpenCV's result).  Runs first: every pixel points at the start of its horizontal run (one warp per row,
+// ballot + clz), then only the non-redundant vertical edges are united (an edge is redundant when the pixel to the left
+// closes a 4-cycle of edges), then sizes are accumulated with warp-aggregated atomics.
+__global__ void __launch_bounds__(256) k_ccl_rows(const int16_t* __restrict__ img, int32_t* label, int32_t* csize, int W, int H,
+                                                  int maxDiff, size_t img_stride, size_t ws_stride) {
+    const int lane = threadIdx.x & 31;
+    const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), f = blockIdx.y;
+    if (y >= H) return;
+    const int16_t* s = frame_ptr(img, img_stride, f) + (size_t)y * W;
+    int32_t* L = frame_ptr(label, ws_stride, f) + (size_t)y * W;
+    int32_t* C = frame_ptr(csize, ws_stride, f) + (size_t)y * W;
+    int carry_start = -1;   // start x of the run that reaches the end of the previous chunk (-1: none)
+    int prev_last = kInv;   // value of the previous chunk's last pixel
+    for (int x0 = 0; x0 < W; x0 += 32) {
+        const int x = x0 + lane;
+        const int v = x < W ? (int)s[x] : kInv;
+        int left = __shfl_up_sync(0xffffffffu, v, 1);
+        if (lane == 0) left = prev_last;
+        const bool valid = v != kInv;
+        const bool link = valid && left != kInv && abs(v - left) <= maxDiff && x > 0;
+        const uint32_t starts = __ballot_sync(0xffffffffu, valid && !link);
+        const uint32_t below = starts & (0xFFFFFFFFu >> (31 - lane));
+        const int start_x = below ? x0 + 31 - __clz((int)below) : carry_start;
+        if (x < W) {
+            L[x] = valid ? y * W + start_x : -1;
+            C[x] = 0;
+        }
+        const int last_start = __shfl_sync(0xffffffffu, valid ? start_x : -1, 31);
+        carry_start = last_start;
+        prev_last = __shfl_sync(0xffffffffu, v, 31);
+    }
 }
-__global__ void k_ccl_merge(const int16_t* __restrict__ img, int32_t* label, int W, int H, int maxDiff, size_t img_stride,
-                            size_t ws_stride) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
-    if (x >= W) return;
+__global__ void k_ccl_vmerge(const int16_t* __restrict__ img, int32_t* label, int W, int H, int maxDiff, size_t img_stride,
+                             size_t ws_stride) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y + 1, f = blockIdx.z;
+    if (x >= W || y >= H) return;
     const int16_t* s = frame_ptr(img, img_stride, f);
-    int32_t* L = frame_ptr(label, ws_stride, f);
     const int i = y * W + x;
-    const int v = s[i];
-    if (v == kInv) return;
-    if (x + 1 < W) { const int q = s[i + 1]; if (q != kInv && abs(v - q) <= maxDiff) ccl_union(L, i, i + 1); }
-    if (y + 1 < H) { const int q = s[i + W]; if (q != kInv && abs(v - q) <= maxDiff) ccl_union(L, i, i + W); }
+    const int v = s[i], u = s[i - W];
+    if (v == kInv || u == kInv || abs(v - u) > maxDiff) return;
+    if (x > 0) {
+        const int vl = s[i - 1], ul = s[i - W - 1];
+        if (vl != kInv && ul != kInv && abs(v - vl) <= maxDiff && abs(u - ul) <= maxDiff && abs(vl - ul) <= maxDiff) return;
+    }
+    ccl_union(frame_ptr(label, ws_stride, f), i, i - W);
 }
 __global__ void k_ccl_count(int32_t* label, int32_t* csize, int n, size_t ws_stride) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x, f = blockIdx.y;
-    if (i >= n) return;
     int32_t* L = frame_ptr(label, ws_stride, f);
-    if (L[i] < 0) return;
-    const int r = ccl_find(L, i);
-    L[i] = r;  // only ever lowers a label towards its root: concurrent finds stay valid
-    atomicAdd(&frame_ptr(csize, ws_stride, f)[r], 1);
+    int r = -1;
+    if (i < n && L[i] >= 0) {
+        r = ccl_find(L, i);
+        L[i] = r;  // only ever lowers a label towards its root: concurrent finds stay valid
+    }
+    const uint32_t peers = __match_any_sync(0xffffffffu, r);
+    if (r >= 0 && (threadIdx.x & 31) == __ffs((int)peers) - 1) atomicAdd(&frame_ptr(csize, ws_stride, f)[r], __popc(peers));
 }
 __global__ void k_ccl_apply(const int16_t* __restrict__ img, const int32_t* __restrict__ label, const int32_t* __restrict__ csize,
                             int16_t* __restrict__ out, int n, int maxSize, size_t img_stride, size_t ws_stride, size_t out_stride) {
@@ -613,10 +643,12 @@ int sgbm_launch(const SgbmDims& d, const SgbmWorkspace* ws0, size_t ws_stride, i
     OVO_LAUNCH(k_median3, gimg, dim3(128), 0, st, ws.raw, ws_stride, ws.med, ws_stride, d.W, d.H);
     OVO_LAUNCH_CHECK();
     dim3 glin(cdiv(n, 256), nb);
-    OVO_LAUNCH(k_ccl_init, glin, dim3(256), 0, st, ws.med, ws.label, ws.csize, n, ws_stride, ws_stride);
+    OVO_LAUNCH(k_ccl_rows, dim3(cdiv(d.H, 8), nb), dim3(256), 0, st, ws.med, ws.label, ws.csize, d.W, d.H, d.speckleDiff, ws_stride, ws_stride);
     OVO_LAUNCH_CHECK();
-    OVO_LAUNCH(k_ccl_merge, gimg, dim3(128), 0, st, ws.med, ws.label, d.W, d.H, d.speckleDiff, ws_stride, ws_stride);
-    OVO_LAUNCH_CHECK();
+    if (d.H > 1) {
+        OVO_LAUNCH(k_ccl_vmerge, dim3(cdiv(d.W, 128), d.H - 1, nb), dim3(128), 0, st, ws.med, ws.label, d.W, d.H, d.speckleDiff, ws_stride, ws_stride);
+        OVO_LAUNCH_CHECK();
+    }
     OVO_LAUNCH(k_ccl_count, glin, dim3(256), 0, st, ws.label, ws.csize, n, ws_stride);
     OVO_LAUNCH_CHECK();
     OVO_LAUNCH(k_ccl_apply, glin, dim3(256), 0, st, ws.med, ws.label, ws.csize, disp_out, n, d.speckleWin, ws_stride, ws_stride, out_stride);

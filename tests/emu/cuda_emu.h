@@ -211,6 +211,12 @@ static inline unsigned __ballot_sync(unsigned, int p) {
     for (int i = 0; i < ovo_emu::warp_lanes(); i++) r |= (b[i] ? 1u : 0u) << i;
     return r;
 }
+static inline unsigned __match_any_sync(unsigned, int v) {
+    const uint64_t* b = ovo_emu::warp_gather((uint64_t)(int64_t)v);
+    unsigned r = 0;
+    for (int i = 0; i < ovo_emu::warp_lanes(); i++) r |= ((int)(int64_t)b[i] == v ? 1u : 0u) << i;
+    return r;
+}
 static inline int __any_sync(unsigned m, int p) { return __ballot_sync(m, p) != 0; }
 static inline int __all_sync(unsigned m, int p) { const int n = ovo_emu::warp_lanes(); return __ballot_sync(m, p) == (n == 32 ? 0xffffffffu : ((1u << n) - 1)); }
 static inline unsigned __reduce_min_sync(unsigned, unsigned v) {
