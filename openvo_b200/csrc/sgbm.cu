@@ -44,21 +44,23 @@ __global__ void k_sgbm_prep(const uint8_t* __restrict__ left, const uint8_t* __r
     const uint8_t* r = I + (size_t)y * pitch;
     const uint8_t* rn = I + (size_t)max(y - 1, 0) * pitch;
     const uint8_t* rs = I + (size_t)min(y + 1, H - 1) * pitch;
-    uint32_t* out = frame_ptr(ws.prep, ws_stride, f) + (size_t)im * 2 * H * W;
+    uint2* out = reinterpret_cast<uint2*>(frame_ptr(ws.prep, ws_stride, f)) + (size_t)im * H * W;
     auto G = [&](int xx) -> int {
         if (xx <= 0 || xx >= W - 1) return ftzero;
         int v = 2 * ((int)r[xx + 1] - (int)r[xx - 1]) + ((int)rn[xx + 1] - (int)rn[xx - 1]) + ((int)rs[xx + 1] - (int)rs[xx - 1]);
         return min(max(v, -ftzero), ftzero) + ftzero;
     };
     auto R = [&](int xx) -> int { return (xx <= 0 || xx >= W - 1) ? ftzero : (int)r[xx]; };
+    uint2 o;
     {
         int c = G(x), vl = x > 0 ? (c + G(x - 1)) >> 1 : c, vr = x < W - 1 ? (c + G(x + 1)) >> 1 : c;
-        out[(size_t)y * W + x] = (uint32_t)c | ((uint32_t)min(min(vl, vr), c) << 8) | ((uint32_t)max(max(vl, vr), c) << 16);
+        o.x = (uint32_t)c | ((uint32_t)min(min(vl, vr), c) << 8) | ((uint32_t)max(max(vl, vr), c) << 16);
     }
     {
         int c = R(x), vl = x > 0 ? (c + R(x - 1)) >> 1 : c, vr = x < W - 1 ? (c + R(x + 1)) >> 1 : c;
-        out[(size_t)H * W + (size_t)y * W + x] = (uint32_t)c | ((uint32_t)min(min(vl, vr), c) << 8) | ((uint32_t)max(max(vl, vr), c) << 16);
+        o.y = (uint32_t)c | ((uint32_t)min(min(vl, vr), c) << 8) | ((uint32_t)max(max(vl, vr), c) << 16);
     }
+    out[(size_t)y * W + x] = o;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -78,6 +80,54 @@ __device__ __forceinline__ uint32_t bt_pair(uint32_t lw, uint32_t rw0, uint32_t 
     return __vminu2(c0, c1);
 }
 
+// one row of a unit: horizontal sums of TX columns, folded into the vertical ring / running sums
+template <int SW2, int TX, bool EDGE>
+__device__ __forceinline__ void cost_row(const uint2* __restrict__ Lrow, const uint2* __restrict__ Rrow, int x0, int d0, int D, int W1,
+                                         bool pad, uint32_t* slot, bool have_old, uint32_t (&vs)[TX]) {
+    constexpr int BS = 2 * SW2 + 1;
+    uint32_t win[BS];
+#pragma unroll
+    for (int i = 0; i < BS; i++) win[i] = 0;
+    uint32_t hs = 0;
+    // interior tiles: all TX + 2*SW2 columns are in range, so every address is a row base plus a compile-time offset and
+    // the right-image word of disparity d+1 is the previous column's word of disparity d
+    const uint2* Lb = Lrow + x0 + D;
+    const uint2* Rb = Rrow + x0 + D - d0;
+    uint2 rprev = make_uint2(0, 0);
+    if (!EDGE && !pad) rprev = __ldg(Rb - SW2 - 1);
+#pragma unroll
+    for (int j = -SW2; j < TX + SW2; j++) {
+        uint32_t pix = 0;
+        if (!pad) {
+            uint2 lw, r0, r1;
+            if (EDGE) {
+                const int xx = min(max(x0 + j, 0), W1 - 1);
+                lw = __ldg(Lrow + xx + D);
+                r0 = __ldg(Rrow + xx + D - d0);
+                r1 = __ldg(Rrow + xx + D - d0 - 1);
+            } else {
+                lw = __ldg(Lb + j);
+                r0 = __ldg(Rb + j);
+                r1 = rprev;
+                rprev = r0;
+            }
+            const uint32_t cg = bt_pair(lw.x, r0.x, r1.x);
+            const uint32_t cr = bt_pair(lw.y, r0.y, r1.y);
+            pix = cg + ((cr >> 2) & 0x3FFF3FFFu);
+        }
+        hs = hs + pix - win[0];
+#pragma unroll
+        for (int i = 0; i < BS - 1; i++) win[i] = win[i + 1];
+        win[BS - 1] = pix;
+        if (j >= SW2) {
+            const int c = j - SW2;
+            const uint32_t old = have_old ? slot[c * kCostThreads] : 0u;
+            vs[c] = vs[c] - old + hs;
+            slot[c * kCostThreads] = hs;
+        }
+    }
+}
+
 template <int SW2, int TX>
 __global__ void __launch_bounds__(kCostThreads) k_sgbm_cost(SgbmDims d, SgbmWorkspace ws, size_t ws_stride) {
     constexpr int BS = 2 * SW2 + 1;
@@ -92,10 +142,11 @@ __global__ void __launch_bounds__(kCostThreads) k_sgbm_cost(SgbmDims d, SgbmWork
     const int W = d.W, H = d.H, D = d.D, W1 = d.W1;
     const int d0 = 2 * threadIdx.x;
     const bool pad = d0 >= D;
-    const uint32_t* prep = frame_ptr(ws.prep, ws_stride, f);
+    const uint2* prep = reinterpret_cast<const uint2*>(frame_ptr(ws.prep, ws_stride, f));
     const size_t plane = (size_t)H * W;
     uint32_t* Cw = reinterpret_cast<uint32_t*>(frame_ptr(ws.C, ws_stride, f));
     const int yend = min(y0 + kCostRS, H);
+    const bool edge = x0 - SW2 < 0 || x0 + TX + SW2 > W1;
 
     uint32_t vs[TX];
 #pragma unroll
@@ -104,36 +155,11 @@ __global__ void __launch_bounds__(kCostThreads) k_sgbm_cost(SgbmDims d, SgbmWork
     int k = 0;  // rows accumulated so far
     for (int r = y0 - SW2; r < yend + SW2; r++, k++) {
         const int yc = min(max(r, 0), H - 1);
-        const uint32_t* Lg = prep + (size_t)yc * W;
-        const uint32_t* Lr = Lg + plane;
-        const uint32_t* Rg = Lg + 2 * plane;
-        const uint32_t* Rr = Lg + 3 * plane;
+        const uint2* Lrow = prep + (size_t)yc * W;
+        const uint2* Rrow = Lrow + plane;
         uint32_t* slot = ring + (size_t)(k % BS) * TX * kCostThreads + tid;
-        uint32_t win[BS];
-#pragma unroll
-        for (int i = 0; i < BS; i++) win[i] = 0;
-        uint32_t hs = 0;
-#pragma unroll
-        for (int j = -SW2; j < TX + SW2; j++) {
-            uint32_t pix = 0;
-            if (!pad) {
-                const int xx = min(max(x0 + j, 0), W1 - 1);
-                const int x = xx + D, xr = x - d0;
-                const uint32_t cg = bt_pair(__ldg(Lg + x), __ldg(Rg + xr), __ldg(Rg + xr - 1));
-                const uint32_t cr = bt_pair(__ldg(Lr + x), __ldg(Rr + xr), __ldg(Rr + xr - 1));
-                pix = cg + ((cr >> 2) & 0x3FFF3FFFu);
-            }
-            hs = hs + pix - win[0];
-#pragma unroll
-            for (int i = 0; i < BS - 1; i++) win[i] = win[i + 1];
-            win[BS - 1] = pix;
-            if (j >= SW2) {
-                const int c = j - SW2;
-                const uint32_t old = k >= BS ? slot[c * kCostThreads] : 0u;
-                vs[c] = vs[c] - old + hs;
-                slot[c * kCostThreads] = hs;
-            }
-        }
+        if (edge) cost_row<SW2, TX, true>(Lrow, Rrow, x0, d0, D, W1, pad, slot, k >= BS, vs);
+        else cost_row<SW2, TX, false>(Lrow, Rrow, x0, d0, D, W1, pad, slot, k >= BS, vs);
         const int y = r - SW2;
         if (y >= y0) {
             uint32_t* out = Cw + ((size_t)y * W1 + x0) * npairs + threadIdx.x;
@@ -146,6 +172,8 @@ __global__ void __launch_bounds__(kCostThreads) k_sgbm_cost(SgbmDims d, SgbmWork
 
 // ------------------------------------------------------------------------------------------------------------
 // A.4.3 one path step on a warp-wide cost vector.  Lane l owns d in [2*NPR*l, 2*NPR*(l+1)), two per register.
+// A predecessor outside the image is the all-zero vector with min 0, for which the step formula yields L = C, so path
+// (re)starts are just a state reset followed by the ordinary step.
 // ------------------------------------------------------------------------------------------------------------
 template <int NPR>
 struct PathState {
@@ -160,13 +188,13 @@ __device__ __forceinline__ void path_reset(PathState<NPR>& s) {
     s.m = 0;
 }
 
-template <int NPR>
+template <int NPR, bool PAD>
 __device__ __forceinline__ void path_step(PathState<NPR>& s, const uint32_t (&c)[NPR], const uint32_t (&padmask)[NPR],
-                                          uint32_t P1P1, uint32_t P2, int lane) {
+                                          uint32_t P1P1, uint32_t P2, bool lane_first, bool lane_last) {
     uint32_t below = __shfl_up_sync(0xffffffffu, s.L[NPR - 1], 1);  // neighbour lane's top pair
     uint32_t above = __shfl_down_sync(0xffffffffu, s.L[0], 1);      // neighbour lane's bottom pair
-    if (lane == 0) below = kMaxC2;                                   // Lp[-1] = MAX_COST
-    if (lane == 31) above = kMaxC2;                                  // Lp[D]  = MAX_COST
+    if (lane_first) below = kMaxC2;                                  // Lp[-1] = MAX_COST
+    if (lane_last) above = kMaxC2;                                   // Lp[D]  = MAX_COST
     const uint32_t mP2 = bcast16(s.m + P2), mm = bcast16(s.m);
     uint32_t out[NPR];
 #pragma unroll
@@ -176,25 +204,14 @@ __device__ __forceinline__ void path_step(PathState<NPR>& s, const uint32_t (&c)
         uint32_t t = __viaddmin_u16x2(dm1, P1P1, s.L[r]);
         t = __viaddmin_u16x2(dp1, P1P1, t);
         t = __vminu2(t, mP2);
-        out[r] = (c[r] + (t - mm)) | padmask[r];
+        out[r] = c[r] + (t - mm);
+        if (PAD) out[r] |= padmask[r];
     }
     uint32_t t = out[0];
 #pragma unroll
     for (int r = 0; r < NPR; r++) {
         s.L[r] = out[r];
         if (r) t = __vminu2(t, out[r]);
-    }
-    s.m = __reduce_min_sync(0xffffffffu, min(t & 0xFFFFu, t >> 16));
-}
-
-template <int NPR>
-__device__ __forceinline__ void path_start(PathState<NPR>& s, const uint32_t (&c)[NPR], const uint32_t (&padmask)[NPR]) {
-    // predecessor outside the image: L = C
-    uint32_t t = kMaxC2;
-#pragma unroll
-    for (int r = 0; r < NPR; r++) {
-        s.L[r] = c[r] | padmask[r];
-        t = __vminu2(t, s.L[r]);
     }
     s.m = __reduce_min_sync(0xffffffffu, min(t & 0xFFFFu, t >> 16));
 }
@@ -226,55 +243,88 @@ __device__ __forceinline__ void stv(uint32_t* p, const uint32_t (&v)[NPR]) {
 
 // ------------------------------------------------------------------------------------------------------------
 // Paths 1..3 (top -> bottom).  One warp per scan line; a diagonal line that leaves the image on one side re-enters
-// on the other with a fresh (zero) predecessor, so every warp does exactly H steps.
+// on the other with a fresh (zero) predecessor, so every warp does exactly H steps.  Cell offsets are 32-bit word
+// offsets inside one frame's volume (< 2^32 words up to 4K / 256 disparities).
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kVertPF = 8;
 
-template <int NPR>
+template <int NPR, bool PAD, int DIR>
+__device__ __forceinline__ void vert_line(const SgbmDims& d, const uint32_t* __restrict__ C, uint32_t* __restrict__ Lout, int line,
+                                          int lane) {
+    constexpr int WPC = 32 * NPR;  // words per cell
+    constexpr int STEP = DIR == 0 ? 1 : (DIR == 2 ? -1 : 0);
+    const int W1 = d.W1, H = d.H;
+    const int xreset = DIR == 0 ? 0 : (DIR == 2 ? W1 - 1 : -1);
+    const ptrdiff_t rowstride = (ptrdiff_t)W1 * WPC;
+    // pointer / column of the next row of this scan line (wraps around the image, which is where the path restarts)
+    auto next_row = [&](int& x, auto*& p) {
+        p += rowstride + STEP * WPC;
+        if (STEP != 0) {
+            x += STEP;
+            if (STEP > 0 && x == W1) { x = 0; p -= rowstride; }
+            if (STEP < 0 && x < 0) { x = W1 - 1; p += rowstride; }
+        }
+    };
+    uint32_t padmask[NPR];
+    make_padmask<NPR>(padmask, lane, d.D);
+    const uint32_t P1P1 = bcast16(d.P1), P2 = d.P2;
+    const bool lane_first = lane == 0, lane_last = lane == 31;
+
+    uint32_t cbuf[kVertPF][NPR];
+    int xpf = line, x = line;
+    const uint32_t* ppf = C + (size_t)line * WPC;
+    uint32_t* pl = Lout + (size_t)line * WPC;
+#pragma unroll
+    for (int i = 0; i < kVertPF; i++) {
+        if (i < H) ldv<NPR>(cbuf[i], ppf);
+        next_row(xpf, ppf);
+    }
+    PathState<NPR> s;
+    path_reset<NPR>(s);
+    int y = 0;
+    for (; y + 2 * kVertPF <= H; y += kVertPF) {  // every step and every prefetch of this group is in range
+#pragma unroll
+        for (int i = 0; i < kVertPF; i++) {
+            uint32_t c[NPR];
+#pragma unroll
+            for (int r = 0; r < NPR; r++) c[r] = cbuf[i][r];
+            ldv<NPR>(cbuf[i], ppf);
+            next_row(xpf, ppf);
+            if (STEP != 0 && x == xreset) path_reset<NPR>(s);
+            path_step<NPR, PAD>(s, c, padmask, P1P1, P2, lane_first, lane_last);
+            stv<NPR>(pl, s.L);
+            next_row(x, pl);
+        }
+    }
+    for (; y < H; y += kVertPF) {
+#pragma unroll
+        for (int i = 0; i < kVertPF; i++) {
+            if (y + i < H) {
+                uint32_t c[NPR];
+#pragma unroll
+                for (int r = 0; r < NPR; r++) c[r] = cbuf[i][r];
+                if (y + i + kVertPF < H) ldv<NPR>(cbuf[i], ppf);
+                next_row(xpf, ppf);
+                if (STEP != 0 && x == xreset) path_reset<NPR>(s);
+                path_step<NPR, PAD>(s, c, padmask, P1P1, P2, lane_first, lane_last);
+                stv<NPR>(pl, s.L);
+                next_row(x, pl);
+            }
+        }
+    }
+}
+
+template <int NPR, bool PAD>
 __global__ void __launch_bounds__(256) k_sgbm_vert(SgbmDims d, SgbmWorkspace ws, size_t ws_stride) {
     const int lane = threadIdx.x & 31;
     const int line = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int dir = blockIdx.y, f = blockIdx.z;
-    const int W1 = d.W1, H = d.H;
-    if (line >= W1) return;
-    constexpr int WPC = 32 * NPR;  // words per cell
+    if (line >= d.W1) return;
     const uint32_t* C = reinterpret_cast<const uint32_t*>(frame_ptr(ws.C, ws_stride, f)) + lane * NPR;
-    uint32_t* Lout = reinterpret_cast<uint32_t*>(frame_ptr(ws.Lv, ws_stride, f)) + (size_t)dir * H * W1 * WPC + lane * NPR;
-    const int step = dir == 0 ? 1 : (dir == 2 ? -1 : 0);
-    auto advance = [&](int x) { x += step; return x >= W1 ? 0 : (x < 0 ? W1 - 1 : x); };
-    const int xreset = dir == 0 ? 0 : (dir == 2 ? W1 - 1 : -1);
-
-    uint32_t padmask[NPR];
-    make_padmask<NPR>(padmask, lane, d.D);
-    const uint32_t P1P1 = bcast16(d.P1), P2 = d.P2;
-
-    uint32_t cbuf[kVertPF][NPR];
-    int xpf = line;
-#pragma unroll
-    for (int i = 0; i < kVertPF; i++) {
-        if (i < H) ldv<NPR>(cbuf[i], C + ((size_t)i * W1 + xpf) * WPC);
-        xpf = advance(xpf);
-    }
-    PathState<NPR> s;
-    path_reset<NPR>(s);
-    int x = line;
-    for (int y0 = 0; y0 < H; y0 += kVertPF) {
-#pragma unroll
-        for (int i = 0; i < kVertPF; i++) {
-            const int y = y0 + i;
-            if (y < H) {
-                uint32_t c[NPR];
-#pragma unroll
-                for (int r = 0; r < NPR; r++) c[r] = cbuf[i][r];
-                if (y + kVertPF < H) ldv<NPR>(cbuf[i], C + ((size_t)(y + kVertPF) * W1 + xpf) * WPC);
-                xpf = advance(xpf);
-                if (y == 0 || x == xreset) path_start<NPR>(s, c, padmask);
-                else path_step<NPR>(s, c, padmask, P1P1, P2, lane);
-                stv<NPR>(Lout + ((size_t)y * W1 + x) * WPC, s.L);
-                x = advance(x);
-            }
-        }
-    }
+    uint32_t* Lout = reinterpret_cast<uint32_t*>(frame_ptr(ws.Lv, ws_stride, f)) + (size_t)dir * d.H * d.W1 * (32 * NPR) + lane * NPR;
+    if (dir == 0) vert_line<NPR, PAD, 0>(d, C, Lout, line, lane);
+    else if (dir == 1) vert_line<NPR, PAD, 1>(d, C, Lout, line, lane);
+    else vert_line<NPR, PAD, 2>(d, C, Lout, line, lane);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -286,57 +336,68 @@ __global__ void __launch_bounds__(256) k_sgbm_vert(SgbmDims d, SgbmWorkspace ws,
 constexpr int kHorPF = 4;
 
 template <int NPR>
-__device__ __forceinline__ void wta_cell(const uint32_t (&S)[NPR], int lane, const SgbmDims& d, int x1, int16_t* disp1s,
-                                         uint32_t* d2key) {
+__device__ __forceinline__ uint32_t half_of(const uint32_t (&S)[NPR], int k) {  // k = 2*r + h, compile-time after unrolling
+    return (k & 1) ? (S[k >> 1] >> 16) : (S[k >> 1] & 0xFFFFu);
+}
+
+// Per-cell selection, serial part only: argmin, the runner-up over |d-best| > 1 (for the uniqueness test) and the two
+// neighbours of the minimum are reduced here and parked in shared memory; the uniqueness decision, the sub-pixel
+// division and the disp2 update are order-independent and run data-parallel over the row afterwards.
+template <int NPR, bool PAD>
+__device__ __forceinline__ void wta_cell(const uint32_t (&S)[NPR], int lane, const SgbmDims& d, int x1, uint32_t* selA,
+                                         uint32_t* selB, uint16_t* selBest) {
     const int D = d.D;
+    const int dd0 = 2 * NPR * lane;
+    // first d minimising S: the smallest (S << 9 | d)
     uint32_t kbest = 0xFFFFFFFFu;
 #pragma unroll
-    for (int r = 0; r < NPR; r++) {
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const uint32_t v = (S[r] >> (16 * h)) & 0xFFFFu;
-            const int dd = 2 * (NPR * lane + r) + h;
-            if (dd < D) kbest = min(kbest, (v << 9) | (uint32_t)dd);
-        }
+    for (int k = 0; k < 2 * NPR; k++) {
+        const uint32_t key = half_of<NPR>(S, k) * 512u + (uint32_t)(dd0 + k);
+        if (!PAD || dd0 + k < D) kbest = min(kbest, key);
     }
     const uint32_t kmin = __reduce_min_sync(0xffffffffu, kbest);
     const int minS = (int)(kmin >> 9), best = (int)(kmin & 511u);
-    bool bad = false;
-    uint32_t sm1 = 0, sp1 = 0;
-    const int lim = minS * 100, fac = 100 - d.uniq;
+    const int fac = 100 - d.uniq;
+    uint32_t m2 = 0xFFFFu;
+    if (fac > 0) {  // exists d, |d-best|>1, S[d]*fac < minS*100  <=>  (min over those d) * fac < minS*100
 #pragma unroll
-    for (int r = 0; r < NPR; r++) {
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int v = (int)((S[r] >> (16 * h)) & 0xFFFFu);
-            const int dd = 2 * (NPR * lane + r) + h;
-            if (dd < D) {
-                if (v * fac < lim && abs(dd - best) > 1) bad = true;
-                if (dd == best - 1) sm1 = (uint32_t)v;
-                if (dd == best + 1) sp1 = (uint32_t)v;
-            }
+        for (int k = 0; k < 2 * NPR; k++) {
+            const bool far = (uint32_t)(dd0 + k - best + 1) > 2u && (!PAD || dd0 + k < D);
+            m2 = min(m2, far ? half_of<NPR>(S, k) : 0xFFFFu);
         }
+        m2 = __reduce_min_sync(0xffffffffu, m2);
+    } else {        // uniquenessRatio >= 100: evaluate the predicate as written; park 0 = reject, 0xFFFF = accept
+        bool bad = false;
+#pragma unroll
+        for (int k = 0; k < 2 * NPR; k++)
+            if ((!PAD || dd0 + k < D) && (int)half_of<NPR>(S, k) * fac < minS * 100 && abs(dd0 + k - best) > 1) bad = true;
+        m2 = __any_sync(0xffffffffu, bad) ? 0u : 0xFFFFu;
     }
-    if (__any_sync(0xffffffffu, bad)) return;  // disp1 stays INVALID
-    sm1 = __reduce_max_sync(0xffffffffu, sm1);
-    sp1 = __reduce_max_sync(0xffffffffu, sp1);
+    auto at = [&](int dd) -> uint32_t {  // S[dd], dd warp-uniform
+        const int r = (dd % (2 * NPR)) >> 1;
+        uint32_t w = S[0];
+#pragma unroll
+        for (int rr = 1; rr < NPR; rr++)
+            if (r == rr) w = S[rr];
+        w = __shfl_sync(0xffffffffu, w, dd / (2 * NPR));
+        return (dd & 1) ? (w >> 16) : (w & 0xFFFFu);
+    };
+    const uint32_t sm1 = at(max(best - 1, 0)), sp1 = at(min(best + 1, D - 1));
     if (lane == 0) {
-        const int x = x1 + D;
-        if (minS < 32767) atomicMin(&d2key[x - best], ((uint32_t)minS << 16) | (uint32_t)(0xFFFF - best));
-        int dsp = best * 16;
-        if (best > 0 && best < D - 1) {
-            const int den = max((int)sm1 + (int)sp1 - 2 * minS, 1);
-            dsp += (((int)sm1 - (int)sp1) * 16 + den) / (2 * den);
-        }
-        disp1s[x] = (int16_t)dsp;
+        selA[x1] = (uint32_t)minS | (m2 << 16);
+        selB[x1] = sm1 | (sp1 << 16);
+        selBest[x1] = (uint16_t)best;
     }
 }
 
-template <int NPR>
+template <int NPR, bool PAD>
 __global__ void __launch_bounds__(64) k_sgbm_horiz(SgbmDims d, SgbmWorkspace ws, size_t ws_stride) {
     OVO_DYN_SMEM(uint32_t, hsm);
     uint32_t* d2key = hsm;                                        // [W]
-    int16_t* disp1s = reinterpret_cast<int16_t*>(hsm + d.W);      // [W]
+    uint32_t* selA = hsm + d.W;                                   // [W1] minS | runner-up << 16
+    uint32_t* selB = selA + d.W1;                                 // [W1] S[best-1] | S[best+1] << 16
+    int16_t* disp1s = reinterpret_cast<int16_t*>(selB + d.W1);    // [W]
+    uint16_t* selBest = reinterpret_cast<uint16_t*>(disp1s + d.W);  // [W1]
     const int y = blockIdx.x, f = blockIdx.y;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int W = d.W, W1 = d.W1, H = d.H;
@@ -350,51 +411,58 @@ __global__ void __launch_bounds__(64) k_sgbm_horiz(SgbmDims d, SgbmWorkspace ws,
     const size_t rowoff = (size_t)y * W1 * WPC + lane * NPR;
     const size_t vol = (size_t)H * W1 * WPC;
     const uint32_t* C = reinterpret_cast<const uint32_t*>(frame_ptr(ws.C, ws_stride, f)) + rowoff;
-    uint32_t* Lv = reinterpret_cast<uint32_t*>(frame_ptr(ws.Lv, ws_stride, f)) + rowoff;
-    uint32_t* T = Lv + vol;  // Lv[1] doubles as the rendezvous scratch
+    const uint32_t* L1 = reinterpret_cast<const uint32_t*>(frame_ptr(ws.Lv, ws_stride, f)) + rowoff;
+    uint32_t* T = const_cast<uint32_t*>(L1) + vol;  // Lv[1] doubles as the rendezvous scratch
+    const uint32_t* L3 = L1 + 2 * vol;
 
     uint32_t padmask[NPR];
     make_padmask<NPR>(padmask, lane, d.D);
     const uint32_t P1P1 = bcast16(d.P1), P2 = d.P2;
+    const bool lane_first = lane == 0, lane_last = lane == 31;
     const int mid = W1 >> 1;
     const int dirx = wid == 0 ? 1 : -1;
     const int xa = wid == 0 ? 0 : W1 - 1;               // first cell of phase 1
     const int n1 = wid == 0 ? mid : W1 - mid;           // cells in phase 1
     const int n2 = W1 - n1;                             // cells in phase 2
+    const ptrdiff_t dstep = dirx * WPC;                 // word step between consecutive cells of this warp
 
     PathState<NPR> s;
     path_reset<NPR>(s);
     // ---- phase 1: T = sat(L1 + L2 + L3 + own)
     {
         uint32_t cb[kHorPF][NPR], l1[kHorPF][NPR], l2[kHorPF][NPR], l3[kHorPF][NPR];
+        const uint32_t *pc = C + xa * WPC, *p1 = L1 + xa * WPC, *p3 = L3 + xa * WPC;
+        const uint32_t* p2 = T + xa * WPC;
+        uint32_t* po = T + xa * WPC;
 #pragma unroll
-        for (int i = 0; i < kHorPF; i++)
-            if (i < n1) {
-                const size_t o = (size_t)(xa + dirx * i) * WPC;
-                ldv<NPR>(cb[i], C + o); ldv<NPR>(l1[i], Lv + o); ldv<NPR>(l2[i], Lv + vol + o); ldv<NPR>(l3[i], Lv + 2 * vol + o);
+        for (int i = 0; i < kHorPF; i++) {
+            if (i < n1) { ldv<NPR>(cb[i], pc); ldv<NPR>(l1[i], p1); ldv<NPR>(l2[i], p2); ldv<NPR>(l3[i], p3); }
+            pc += dstep; p1 += dstep; p2 += dstep; p3 += dstep;
+        }
+        auto body = [&](int i, bool pf) {
+            uint32_t c[NPR], sv[NPR];
+#pragma unroll
+            for (int r = 0; r < NPR; r++) {
+                c[r] = cb[i][r];
+                sv[r] = __viaddmin_u16x2(__viaddmin_u16x2(l1[i][r], l2[i][r], kMaxC2), l3[i][r], kMaxC2);
             }
-        for (int k0 = 0; k0 < n1; k0 += kHorPF) {
+            if (pf) { ldv<NPR>(cb[i], pc); ldv<NPR>(l1[i], p1); ldv<NPR>(l2[i], p2); ldv<NPR>(l3[i], p3); }
+            pc += dstep; p1 += dstep; p2 += dstep; p3 += dstep;
+            path_step<NPR, PAD>(s, c, padmask, P1P1, P2, lane_first, lane_last);
 #pragma unroll
-            for (int i = 0; i < kHorPF; i++) {
-                const int k = k0 + i;
-                if (k < n1) {
-                    uint32_t c[NPR], sv[NPR];
+            for (int r = 0; r < NPR; r++) sv[r] = __viaddmin_u16x2(sv[r], s.L[r], kMaxC2);
+            stv<NPR>(po, sv);
+            po += dstep;
+        };
+        int k = 0;
+        for (; k + 2 * kHorPF <= n1; k += kHorPF) {
 #pragma unroll
-                    for (int r = 0; r < NPR; r++) {
-                        c[r] = cb[i][r];
-                        sv[r] = __viaddmin_u16x2(__viaddmin_u16x2(l1[i][r], l2[i][r], kMaxC2), l3[i][r], kMaxC2);
-                    }
-                    if (k + kHorPF < n1) {
-                        const size_t o = (size_t)(xa + dirx * (k + kHorPF)) * WPC;
-                        ldv<NPR>(cb[i], C + o); ldv<NPR>(l1[i], Lv + o); ldv<NPR>(l2[i], Lv + vol + o); ldv<NPR>(l3[i], Lv + 2 * vol + o);
-                    }
-                    if (k == 0) path_start<NPR>(s, c, padmask);
-                    else path_step<NPR>(s, c, padmask, P1P1, P2, lane);
+            for (int i = 0; i < kHorPF; i++) body(i, true);
+        }
+        for (; k < n1; k += kHorPF) {
 #pragma unroll
-                    for (int r = 0; r < NPR; r++) sv[r] = __viaddmin_u16x2(sv[r], s.L[r], kMaxC2);
-                    stv<NPR>(T + (size_t)(xa + dirx * k) * WPC, sv);
-                }
-            }
+            for (int i = 0; i < kHorPF; i++)
+                if (k + i < n1) body(i, k + i + kHorPF < n1);
         }
     }
     __syncthreads();
@@ -402,31 +470,55 @@ __global__ void __launch_bounds__(64) k_sgbm_horiz(SgbmDims d, SgbmWorkspace ws,
     {
         const int xb = xa + dirx * n1;
         uint32_t cb[kHorPF][NPR], tb[kHorPF][NPR];
+        const uint32_t *pc = C + xb * WPC, *pt = T + xb * WPC;
 #pragma unroll
-        for (int i = 0; i < kHorPF; i++)
-            if (i < n2) {
-                const size_t o = (size_t)(xb + dirx * i) * WPC;
-                ldv<NPR>(cb[i], C + o); ldv<NPR>(tb[i], T + o);
+        for (int i = 0; i < kHorPF; i++) {
+            if (i < n2) { ldv<NPR>(cb[i], pc); ldv<NPR>(tb[i], pt); }
+            pc += dstep; pt += dstep;
+        }
+        int x1 = xb;
+        if (n1 == 0) path_reset<NPR>(s);
+        auto body = [&](int i, bool pf) {
+            uint32_t c[NPR], S[NPR];
+#pragma unroll
+            for (int r = 0; r < NPR; r++) { c[r] = cb[i][r]; S[r] = tb[i][r]; }
+            if (pf) { ldv<NPR>(cb[i], pc); ldv<NPR>(tb[i], pt); }
+            pc += dstep; pt += dstep;
+            path_step<NPR, PAD>(s, c, padmask, P1P1, P2, lane_first, lane_last);
+#pragma unroll
+            for (int r = 0; r < NPR; r++) S[r] = __viaddmin_u16x2(S[r], s.L[r], kMaxC2);
+            wta_cell<NPR, PAD>(S, lane, d, x1, selA, selB, selBest);
+            x1 += dirx;
+        };
+        int k = 0;
+        for (; k + 2 * kHorPF <= n2; k += kHorPF) {
+#pragma unroll
+            for (int i = 0; i < kHorPF; i++) body(i, true);
+        }
+        for (; k < n2; k += kHorPF) {
+#pragma unroll
+            for (int i = 0; i < kHorPF; i++)
+                if (k + i < n2) body(i, k + i + kHorPF < n2);
+        }
+    }
+    __syncthreads();
+    // ---- uniqueness, sub-pixel refinement and disp2 (A.4.4), data-parallel over the row
+    {
+        const int D = d.D, fac = 100 - d.uniq;
+        for (int x1 = threadIdx.x; x1 < W1; x1 += blockDim.x) {
+            const uint32_t a = selA[x1], b = selB[x1];
+            const int minS = (int)(a & 0xFFFFu), m2 = (int)(a >> 16), best = selBest[x1];
+            const bool reject = fac > 0 ? (m2 * fac < minS * 100) : (m2 == 0);
+            if (reject) continue;
+            const int x = x1 + D;
+            if (minS < 32767) atomicMin(&d2key[x - best], ((uint32_t)minS << 16) | (uint32_t)(0xFFFF - best));
+            int dsp = best * 16;
+            if (best > 0 && best < D - 1) {
+                const int sm1 = (int)(b & 0xFFFFu), sp1 = (int)(b >> 16);
+                const int den = max(sm1 + sp1 - 2 * minS, 1);
+                dsp += ((sm1 - sp1) * 16 + den) / (2 * den);
             }
-        for (int k0 = 0; k0 < n2; k0 += kHorPF) {
-#pragma unroll
-            for (int i = 0; i < kHorPF; i++) {
-                const int k = k0 + i;
-                if (k < n2) {
-                    uint32_t c[NPR], S[NPR];
-#pragma unroll
-                    for (int r = 0; r < NPR; r++) { c[r] = cb[i][r]; S[r] = tb[i][r]; }
-                    if (k + kHorPF < n2) {
-                        const size_t o = (size_t)(xb + dirx * (k + kHorPF)) * WPC;
-                        ldv<NPR>(cb[i], C + o); ldv<NPR>(tb[i], T + o);
-                    }
-                    if (n1 == 0 && k == 0) path_start<NPR>(s, c, padmask);
-                    else path_step<NPR>(s, c, padmask, P1P1, P2, lane);
-#pragma unroll
-                    for (int r = 0; r < NPR; r++) S[r] = __viaddmin_u16x2(S[r], s.L[r], kMaxC2);
-                    wta_cell<NPR>(S, lane, d, xb + dirx * k, disp1s, d2key);
-                }
-            }
+            disp1s[x] = (int16_t)dsp;
         }
     }
     __syncthreads();
@@ -564,14 +656,16 @@ __global__ void k_ccl_apply(const int16_t* __restrict__ img, const int32_t* __re
     frame_ptr(out, out_stride, f)[i] = o;
 }
 
-template <int NPR>
+template <int NPR, bool PAD>
 int launch_paths(const SgbmDims& d, const SgbmWorkspace& ws, size_t ws_stride, int nb, cudaStream_t st) {
     dim3 gv(cdiv(d.W1, 8), 3, nb);
-    { auto k_sgbm_vert_t = k_sgbm_vert<NPR>; OVO_LAUNCH(k_sgbm_vert_t, gv, dim3(256), 0, st, d, ws, ws_stride); }
+    { auto k_sgbm_vert_t = k_sgbm_vert<NPR, PAD>; OVO_LAUNCH(k_sgbm_vert_t, gv, dim3(256), 0, st, d, ws, ws_stride); }
     OVO_LAUNCH_CHECK();
     dim3 gh(d.H, nb);
-    const size_t smem = (size_t)d.W * 4 + (size_t)d.W * 2 + 16;
-    { auto k_sgbm_horiz_t = k_sgbm_horiz<NPR>; OVO_LAUNCH(k_sgbm_horiz_t, gh, dim3(64), smem, st, d, ws, ws_stride); }
+    const size_t smem = (size_t)d.W * 6 + (size_t)d.W1 * 10 + 16;
+    { auto k_sgbm_horiz_t = k_sgbm_horiz<NPR, PAD>;
+      if (smem > 48 * 1024) OVO_CUDA(cudaFuncSetAttribute(k_sgbm_horiz_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      OVO_LAUNCH(k_sgbm_horiz_t, gh, dim3(64), smem, st, d, ws, ws_stride); }
     OVO_LAUNCH_CHECK();
     return 0;
 }
@@ -626,9 +720,9 @@ int sgbm_launch(const SgbmDims& d, const SgbmWorkspace* ws0, size_t ws_stride, i
     }
     if (rc) return rc;
     switch (d.Dp) {
-        case 64: rc = launch_paths<1>(d, ws, ws_stride, nb, st); break;
-        case 128: rc = launch_paths<2>(d, ws, ws_stride, nb, st); break;
-        case 256: rc = launch_paths<4>(d, ws, ws_stride, nb, st); break;
+        case 64: rc = d.D == 64 ? launch_paths<1, false>(d, ws, ws_stride, nb, st) : launch_paths<1, true>(d, ws, ws_stride, nb, st); break;
+        case 128: rc = d.D == 128 ? launch_paths<2, false>(d, ws, ws_stride, nb, st) : launch_paths<2, true>(d, ws, ws_stride, nb, st); break;
+        case 256: rc = d.D == 256 ? launch_paths<4, false>(d, ws, ws_stride, nb, st) : launch_paths<4, true>(d, ws, ws_stride, nb, st); break;
         default: set_error("padded disparity range %d unsupported", d.Dp); return 1;
     }
     if (rc) return rc;
