@@ -170,6 +170,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="K", choices=list(CONFIGS))
     ap.add_argument("--seqs", type=int, default=8, help="independent sequences (= frames per step) per GPU")
+    ap.add_argument("--threads", type=int, default=2, help="host threads (each with its own CUDA stream and share of the sequences)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--_cpu_worker", nargs=5, default=None)
     a = ap.parse_args()
@@ -226,16 +227,21 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    NT = max(1, min(a.threads, S))
+    assert S % NT == 0, "--seqs must be divisible by --threads"
+    SP = S // NT  # sequences per host thread
+    streams = [torch.cuda.Stream() for _ in range(NT)]
+
     def fresh():
-        return BatchOdometer(cam, S, nfeatures=cfg["n"], preprocessed_frames=True)
+        return [BatchOdometer(cam, SP, nfeatures=cfg["n"], engine_tag=t, preprocessed_frames=True) for t in range(NT)]
 
     dev_L, dev_R = torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()
     lib = _native.load()
 
-    def run(bo, steps, first_step, host):
+    def run_part(bo, t, steps, first_step, host):
         ok = 0
         for s in range(first_step, first_step + steps):
-            idx = [frame_index(s, rank * S + q) for q in range(S)]
+            idx = [frame_index(s, rank * S + t * SP + q) for q in range(SP)]
             if host:
                 res = bo.update(L[idx], R[idx])
             else:
@@ -244,19 +250,47 @@ def main():
             ok += sum(res)
         return ok
 
+    def run(bos, steps, first_step, host):
+        """Every host thread drives its share of the sequences on its own stream; host-side work of one (keypoint selection,
+        launches) overlaps device work of the other."""
+        oks, errs = [0] * NT, []
+        torch.cuda.synchronize()
+
+        def work(t):
+            try:
+                torch.cuda.set_device(local_rank)
+                with torch.cuda.stream(streams[t]):
+                    oks[t] = run_part(bos[t], t, steps, first_step, host)
+            except Exception as e:  # pragma: no cover
+                errs.append(e)
+        if NT == 1:
+            work(0)
+        else:
+            th = [threading.Thread(target=work, args=(t,)) for t in range(NT)]
+            for x in th:
+                x.start()
+            for x in th:
+                x.join()
+        if errs:
+            raise errs[0]
+        for st in streams:
+            torch.cuda.current_stream().wait_stream(st)
+        return sum(oks)
+
     def timed(host):
-        bo = fresh()
-        run(bo, warmup, 0, host)
-        eng = bo.engine
-        h2d0, d2h0, l0 = eng.h2d_bytes, eng.d2h_bytes, lib.ovo_launch_count()
+        bos = fresh()
+        run(bos, warmup, 0, host)
+        engs = [b.engine for b in bos]
+        h2d0, d2h0, l0 = sum(e.h2d_bytes for e in engs), sum(e.d2h_bytes for e in engs), lib.ovo_launch_count()
         sampler = ClockSampler(local_rank)
         barrier()
         sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        ok = run(bo, a.steps, warmup, host)
+        ok = run(bos, a.steps, warmup, host)
         if world > 1:  # the only exchange: per-frame relative transforms + status, once per chunk
-            T = np.stack([od.last_T if od.last_T is not None else np.eye(4) for od in bo.odometers])[:, None]
+            ods = [od for b in bos for od in b.odometers]
+            T = np.stack([od.last_T if od.last_T is not None else np.eye(4) for od in ods])[:, None]
             st = np.ones((S, 1), np.int32)
             odist.gather_poses(T, st, odist.shard_sequences(S * world, rank, world), S * world)
         e1.record()
@@ -267,8 +301,8 @@ def main():
             t = torch.tensor([ms], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return dict(ms=ms, ok=ok, h2d=(eng.h2d_bytes - h2d0) / a.steps, d2h=(eng.d2h_bytes - d2h0) / a.steps,
-                    launches=lib.ovo_launch_count() - l0, clocks=clocks, bo=bo)
+        return dict(ms=ms, ok=ok, h2d=(sum(e.h2d_bytes for e in engs) - h2d0) / a.steps, d2h=(sum(e.d2h_bytes for e in engs) - d2h0) / a.steps,
+                    launches=lib.ovo_launch_count() - l0, clocks=clocks, bos=bos)
 
     dev = timed(host=False)
     e2e = timed(host=True)
@@ -279,9 +313,9 @@ def main():
     # ---- roofline leg: per-kernel CUDA-event durations over an identical region (events on the launching stream)
     roofline, per_kernel = None, {}
     if rank == 0:
-        bo = dev["bo"]
+        bos = dev["bos"]
         lib.ovo_profile_enable(1)
-        run(bo, min(a.steps, 5), warmup + a.steps, False)
+        run(bos, min(a.steps, 5), warmup + a.steps, False)
         prof = _native.profile_read(lib)
         lib.ovo_profile_enable(0)
         tot = sum(v[0] for v in prof.values()) or 1.0
@@ -293,7 +327,7 @@ def main():
         except Exception:
             pass
         peak, which = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
-        abytes = algorithmic_bytes(top, bo.engine, S)
+        abytes = algorithmic_bytes(top, bos[0].engine, SP)
         dur_s = prof[top][0] / prof[top][1] * 1e-3
         achieved = abytes / dur_s / 1e9 if dur_s > 0 else 0.0
         traffic = None
@@ -308,7 +342,7 @@ def main():
         line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": a.steps, "warmup": warmup,
                 "ms_per_step": dev["ms"] / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i16",
                 "data": "synthetic",
-                "config": {"workload": workload, "frames_per_step": S * world, "sequences_per_gpu": S, "distinct_frames": N_DISTINCT,
+                "config": {"workload": workload, "frames_per_step": S * world, "sequences_per_gpu": S, "host_threads": NT, "distinct_frames": N_DISTINCT,
                            "l2_policy": "inputs+working set larger than L2: %d frames x ~0.55 GB SGBM volumes per step" % S,
                            "frames_committed": dev["ok"]},
                 "clocks": dev["clocks"], "gpu_launches": dev["launches"],

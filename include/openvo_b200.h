@@ -105,6 +105,21 @@ int ovo_match_points(ovo_ctx* ctx, const int32_t* nn_dev, int nq, double match_t
 int ovo_rigid_transform(ovo_ctx* ctx, const float* pts1_dev, const float* pts2_dev, const int32_t* count_dev, int cap,
                         double* out_dev, void* stream);
 
+/* Batched form of S-E + a8/S-F + S-G for n independent frame pairs (n <= max_batch): 2-NN, ratio test + fused 3-D lookup and
+ * rigid alignment of every pair in four launches.  `items` is a HOST array; all pointers inside are device pointers.
+ * out: f64 [18] per pair = the 16 values of ovo_rigid_transform followed by the two int32 counts of ovo_match_points packed in
+ * slot 16.  `scratch` is filled in by the library. */
+typedef struct ovo_pair_item {
+    const uint8_t *q_desc, *t_desc;
+    int nq, nt;
+    const float *kp1, *kp2, *disp1_f32, *disp2_f32;
+    int32_t *nn, *matches;
+    float *pts1, *pts2;
+    double* out;
+    uint32_t* scratch;
+} ovo_pair_item;
+int ovo_pair_batch(ovo_ctx* ctx, int n, const ovo_pair_item* items_host, double match_threshold, void* stream);
+
 /* Instrumentation for bench.py: number of kernels launched by this library so far; optional per-kernel CUDA-event timing
  * (events recorded on the launching stream around every kernel while enabled).  ovo_profile_read synchronises the device
  * and returns, per kernel name ('\n'-separated in `names`), the summed milliseconds and the launch count since the last

@@ -25,6 +25,13 @@ class Config(ctypes.Structure):
                 ("min_valid_disparity", ctypes.c_float), ("max_valid_disparity", ctypes.c_float)]
 
 
+class PairItem(ctypes.Structure):
+    _fields_ = [("q_desc", ctypes.c_void_p), ("t_desc", ctypes.c_void_p), ("nq", ctypes.c_int), ("nt", ctypes.c_int),
+                ("kp1", ctypes.c_void_p), ("kp2", ctypes.c_void_p), ("disp1", ctypes.c_void_p), ("disp2", ctypes.c_void_p),
+                ("nn", ctypes.c_void_p), ("matches", ctypes.c_void_p), ("pts1", ctypes.c_void_p), ("pts2", ctypes.c_void_p),
+                ("out", ctypes.c_void_p), ("scratch", ctypes.c_void_p)]
+
+
 class NativeError(RuntimeError):
     pass
 
@@ -46,6 +53,7 @@ _SIGNATURES = {
     "ovo_knn2_hamming": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),
     "ovo_match_points": (_i, [_vp, _vp, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ovo_rigid_transform": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "ovo_pair_batch": (_i, [_vp, _i, ctypes.POINTER(PairItem), _d, _vp]),
     "ovo_launch_count": (ctypes.c_longlong, []),
     "ovo_transfer_bytes": (None, [_vp, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong)]),
     "ovo_profile_enable": (None, [_i]),

@@ -9,10 +9,10 @@ from .stereo_odometer import StereoOdometer
 
 
 class BatchOdometer:
-    def __init__(self, stereo_camera, n_sequences, nfeatures=500, **kw):
+    def __init__(self, stereo_camera, n_sequences, nfeatures=500, engine_tag=0, **kw):
         self.n = int(n_sequences)
         self.stereo = stereo_camera
-        self.odometers = [StereoOdometer(stereo_camera, nfeatures=nfeatures, _max_batch=self.n, **kw) for _ in range(self.n)]
+        self.odometers = [StereoOdometer(stereo_camera, nfeatures=nfeatures, _max_batch=self.n, _engine_tag=engine_tag, **kw) for _ in range(self.n)]
         self.engine = self.odometers[0]._engine()
 
     def update(self, lefts, rights):
@@ -24,11 +24,12 @@ class BatchOdometer:
         """Same, with the frames already resident on the device (torch uint8 [S,H,W])."""
         eng = self.engine
         frames = eng.frames(lefts, rights)
-        queued = []
+        queued, jobs = [], []
         for i, (od, fr) in enumerate(zip(self.odometers, frames)):
             if od._cur is not None and fr.n_kp >= od.min_matches and fr.n_kp >= 2:
-                eng.pair_async(od._cur, fr, od.match_threshold, slot=i)
+                jobs.append((od._cur, fr, i))
                 queued.append(i)
+        eng.pair_batch_async(jobs, self.odometers[0].match_threshold)
         res = eng.pair_collect(self.n) if queued else []
         out = []
         for i, (od, fr) in enumerate(zip(self.odometers, frames)):

@@ -58,6 +58,9 @@ int orb_phase2_launch(const OrbDims& d, const OrbWorkspace* ws0, size_t ws_strid
 int reproject_launch(const float* disp, int pitch, int cw, int ch, int x0, int y0, const double* Q16, float* xyz, cudaStream_t st);
 int disp_post_launch(const int16_t* disp, int W, int H, int x0, int y0, int cw, int ch, float lo, float hi, float* disp_f32,
                      uint8_t* mask, int nb, cudaStream_t st);
+int pair_batch_launch(const GatherParams& gp, int n, const void* items_host, int cap, cudaStream_t st);
+int pair_item_size();
+int pair_max_batch();
 int crop_launch(const uint8_t* img, int pitch, size_t frame_stride, int x0, int y0, int cw, int ch, int nb, uint8_t* out, cudaStream_t st);
 
 struct Layout {
@@ -104,7 +107,7 @@ static int make_layout(const ovo_config* c, Layout* L) {
     L->frame_bytes = L->sgbm_bytes + L->orb_bytes;
     orb_make_resize_tables(L->orb, nullptr, L->tab_off, &L->tab_total);
     L->tab_bytes = align_up((size_t)L->tab_total * 4, 256);
-    L->knn_bytes = align_up(knn2_scratch_bytes(L->orb.kp_cap, L->orb.kp_cap), 256);
+    L->knn_bytes = align_up(knn2_scratch_bytes(L->orb.kp_cap, L->orb.kp_cap), 256) * c->max_batch;
     L->nsel_bytes = align_up((size_t)c->max_batch * 4, 256);
     L->total = L->frame_bytes * c->max_batch + L->tab_bytes + L->knn_bytes + L->nsel_bytes + 256;
     return 0;
@@ -332,6 +335,26 @@ int ovo_match_points(ovo_ctx* c, const int32_t* nn, int nq, double thr, const fl
     memcpy(p.Q, c->cfg.Q, sizeof(p.Q));
     p.thr = thr; p.roi_x0 = c->L.x0; p.roi_y0 = c->L.y0; p.cw = c->L.cw; p.ch = c->L.ch; p.disp_pitch = c->L.cw;
     return match_gather_launch(p, nn, nq, kp1, kp2, disp1, disp2, matches, pts1, pts2, counts, (cudaStream_t)stream);
+}
+
+int ovo_pair_batch(ovo_ctx* c, int n, const ovo_pair_item* items, double thr, void* stream) {
+    CHECK_CTX(c, 1);
+    if (sizeof(ovo_pair_item) != (size_t)pair_item_size()) { set_error("ovo_pair_item layout mismatch"); return 1; }
+    if (n < 0 || n > c->cfg.max_batch) { set_error("pair batch %d exceeds max_batch", n); return 1; }
+    GatherParams p;
+    memcpy(p.Q, c->cfg.Q, sizeof(p.Q));
+    p.thr = thr; p.roi_x0 = c->L.x0; p.roi_y0 = c->L.y0; p.cw = c->L.cw; p.ch = c->L.ch; p.disp_pitch = c->L.cw;
+    const size_t per = c->L.knn_bytes / c->cfg.max_batch;
+    for (int i0 = 0; i0 < n; i0 += pair_max_batch()) {
+        const int m = n - i0 < pair_max_batch() ? n - i0 : pair_max_batch();
+        std::vector<ovo_pair_item> tmp(items + i0, items + i0 + m);
+        for (int i = 0; i < m; i++) {
+            if (tmp[i].nq > c->L.orb.kp_cap || tmp[i].nt > c->L.orb.kp_cap) { set_error("descriptor count exceeds keypoint capacity"); return 1; }
+            tmp[i].scratch = (uint32_t*)((uint8_t*)c->knn_scratch + per * (size_t)(i0 + i));
+        }
+        if (pair_batch_launch(p, m, tmp.data(), c->L.orb.kp_cap, (cudaStream_t)stream)) return 1;
+    }
+    return 0;
 }
 
 int ovo_rigid_transform(ovo_ctx* c, const float* pts1, const float* pts2, const int32_t* count, int cap, double* out, void* stream) {

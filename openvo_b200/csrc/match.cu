@@ -8,6 +8,7 @@
 //   cv2.estimateAffine3D(force_rotation=True), Rodrigues norm  ref: :204-221                          (A.5.3-4)
 //   .astype(float32)/16, crop, feature_mask                    ref: stereo_camera.py:51,53-55; stereo_odometer.py:38-41
 #include "common.cuh"
+#include <cstring>
 
 namespace ovo {
 
@@ -56,12 +57,13 @@ constexpr int kKnnQ = 128;     // queries per CTA
 constexpr int kKnnTile = 256;  // train descriptors per stage (8 KB)
 constexpr uint32_t kKeyNone = 0xFFFFFFFFu;
 
-__global__ void __launch_bounds__(kKnnQ) k_knn2_partial(const uint8_t* __restrict__ q, int nq, const uint8_t* __restrict__ t, int nt,
-                                                        int nsplit, uint32_t* __restrict__ part) {
+__device__ __forceinline__ void knn2_partial_body(const uint8_t* __restrict__ q, int nq, const uint8_t* __restrict__ t, int nt,
+                                                  int nsplit, uint32_t* __restrict__ part) {
     __shared__ __align__(128) uint4 tile[2][kKnnTile * 2];
 #ifndef OVO_EMU
     __shared__ __align__(8) uint64_t bar[2];
 #endif
+    if ((int)(blockIdx.x * kKnnQ) >= nq) return;  // whole CTA (batched launches are sized for the largest query set)
     const int qi = blockIdx.x * kKnnQ + threadIdx.x;
     const int split = blockIdx.y;
     const int per = (nt + nsplit - 1) / nsplit;
@@ -121,7 +123,28 @@ __global__ void __launch_bounds__(kKnnQ) k_knn2_partial(const uint8_t* __restric
     }
 }
 
-__global__ void k_knn2_merge(const uint32_t* __restrict__ part, int nq, int nsplit, int32_t* __restrict__ nn) {
+struct PairItem {
+    const uint8_t *q, *t;
+    int nq, nt;
+    const float *kp1, *kp2, *disp1, *disp2;
+    int32_t *nn, *matches;
+    float *pts1, *pts2;
+    double* out;        // [18]: 16 rigid-transform outputs, then two int32 counts in slot 16
+    uint32_t* scratch;  // 2-NN partial results
+};
+constexpr int kMaxPairs = 16;
+struct PairBatch { PairItem it[kMaxPairs]; };
+
+__global__ void __launch_bounds__(kKnnQ) k_knn2_partial(const uint8_t* __restrict__ q, int nq, const uint8_t* __restrict__ t, int nt,
+                                                        int nsplit, uint32_t* __restrict__ part) {
+    knn2_partial_body(q, nq, t, nt, nsplit, part);
+}
+__global__ void __launch_bounds__(kKnnQ) k_knn2_partial_b(PairBatch b, int nsplit) {
+    const PairItem& p = b.it[blockIdx.z];
+    knn2_partial_body(p.q, p.nq, p.t, p.nt, nsplit, p.scratch);
+}
+
+__device__ __forceinline__ void knn2_merge_body(const uint32_t* __restrict__ part, int nq, int nsplit, int32_t* __restrict__ nn) {
     const int qi = blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= nq) return;
     uint32_t k0 = kKeyNone, k1 = kKeyNone;
@@ -136,6 +159,13 @@ __global__ void k_knn2_merge(const uint32_t* __restrict__ part, int nq, int nspl
     o[1] = k0 == kKeyNone ? 0 : (int)(k0 >> 20);
     o[2] = k1 == kKeyNone ? -1 : (int)(k1 & 0xFFFFFu);
     o[3] = k1 == kKeyNone ? 0 : (int)(k1 >> 20);
+}
+__global__ void k_knn2_merge(const uint32_t* __restrict__ part, int nq, int nsplit, int32_t* __restrict__ nn) {
+    knn2_merge_body(part, nq, nsplit, nn);
+}
+__global__ void k_knn2_merge_b(PairBatch b, int nsplit) {
+    const PairItem& p = b.it[blockIdx.z];
+    knn2_merge_body(p.scratch, p.nq, nsplit, p.nn);
 }
 
 // ---- reprojection (A.5.1) ------------------------------------------------------------------------------------------------
@@ -194,11 +224,11 @@ __device__ bool lookup_point(const GatherParams& P, const float* __restrict__ di
     return any;
 }
 
-__global__ void __launch_bounds__(1024) k_match_gather(GatherParams P, const int32_t* __restrict__ nn, int nq,
-                                                       const float* __restrict__ kp1, const float* __restrict__ kp2,
-                                                       const float* __restrict__ disp1, const float* __restrict__ disp2,
-                                                       int32_t* __restrict__ matches, float* __restrict__ pts1, float* __restrict__ pts2,
-                                                       int32_t* __restrict__ counts) {
+__device__ __forceinline__ void match_gather_body(const GatherParams& P, const int32_t* __restrict__ nn, int nq,
+                                                  const float* __restrict__ kp1, const float* __restrict__ kp2,
+                                                  const float* __restrict__ disp1, const float* __restrict__ disp2,
+                                                  int32_t* __restrict__ matches, float* __restrict__ pts1, float* __restrict__ pts2,
+                                                  int32_t* __restrict__ counts) {
     __shared__ int warp_sums[32];
     __shared__ int base_s, bad_s;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -244,6 +274,17 @@ __global__ void __launch_bounds__(1024) k_match_gather(GatherParams P, const int
         __syncthreads();
     }
     if (threadIdx.x == 0) { counts[0] = base_s; counts[1] = bad_s; }
+}
+__global__ void __launch_bounds__(1024) k_match_gather(GatherParams P, const int32_t* __restrict__ nn, int nq,
+                                                       const float* __restrict__ kp1, const float* __restrict__ kp2,
+                                                       const float* __restrict__ disp1, const float* __restrict__ disp2,
+                                                       int32_t* __restrict__ matches, float* __restrict__ pts1, float* __restrict__ pts2,
+                                                       int32_t* __restrict__ counts) {
+    match_gather_body(P, nn, nq, kp1, kp2, disp1, disp2, matches, pts1, pts2, counts);
+}
+__global__ void __launch_bounds__(1024) k_match_gather_b(GatherParams P, PairBatch b) {
+    const PairItem& p = b.it[blockIdx.x];
+    match_gather_body(P, p.nn, p.nq, p.kp1, p.kp2, p.disp1, p.disp2, p.matches, p.pts1, p.pts2, reinterpret_cast<int32_t*>(p.out + 16));
 }
 
 // ---- Umeyama (A.5.3) ---------------------------------------------------------------------------------------------------------
@@ -310,8 +351,8 @@ __device__ __forceinline__ double det3(const double* m) {
     return m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
 }
 
-__global__ void __launch_bounds__(256) k_umeyama(const float* __restrict__ src, const float* __restrict__ dst, const int32_t* __restrict__ count,
-                                                 int cap, double* __restrict__ out) {
+__device__ __forceinline__ void umeyama_body(const float* __restrict__ src, const float* __restrict__ dst, const int32_t* __restrict__ count,
+                                             int cap, double* __restrict__ out) {
     __shared__ double sh[256];
     __shared__ double mu[6];
     const int n = min(*count, cap);
@@ -361,6 +402,14 @@ __global__ void __launch_bounds__(256) k_umeyama(const float* __restrict__ src, 
     out[14] = sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
     out[15] = (double)n;
 }
+__global__ void __launch_bounds__(256) k_umeyama(const float* __restrict__ src, const float* __restrict__ dst, const int32_t* __restrict__ count,
+                                                 int cap, double* __restrict__ out) {
+    umeyama_body(src, dst, count, cap, out);
+}
+__global__ void __launch_bounds__(256) k_umeyama_b(PairBatch b, int cap) {
+    const PairItem& p = b.it[blockIdx.x];
+    umeyama_body(p.pts1, p.pts2, reinterpret_cast<const int32_t*>(p.out + 16), cap, p.out);
+}
 
 // ---- small glue -----------------------------------------------------------------------------------------------------------------
 __global__ void k_disp_post(const int16_t* __restrict__ disp, int W, int x0, int y0, int cw, int ch, float lo, float hi,
@@ -395,6 +444,34 @@ int knn2_launch(const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* nn_
     OVO_LAUNCH_CHECK();
     return 0;
 }
+
+// n <= kMaxPairs frame pairs in four launches: 2-NN partial / merge, ratio + gather, rigid alignment
+int pair_batch_launch(const GatherParams& gp, int n, const void* items_host, int cap, cudaStream_t st) {
+    PairBatch b;
+    memset(&b, 0, sizeof(b));
+    memcpy(b.it, items_host, sizeof(PairItem) * n);
+    int maxq = 0, maxt = 0;
+    for (int i = 0; i < n; i++) {
+        maxq = b.it[i].nq > maxq ? b.it[i].nq : maxq;
+        maxt = b.it[i].nt > maxt ? b.it[i].nt : maxt;
+        if (b.it[i].nt >= (1 << 20)) { set_error("knn2: train set too large"); return 1; }
+    }
+    if (maxq > 0) {
+        int nsplit = cdiv(maxt, 128);
+        nsplit = nsplit < 1 ? 1 : (nsplit > 32 ? 32 : nsplit);
+        OVO_LAUNCH(k_knn2_partial_b, dim3(cdiv(maxq, kKnnQ), nsplit, n), dim3(kKnnQ), 0, st, b, nsplit);
+        OVO_LAUNCH_CHECK();
+        OVO_LAUNCH(k_knn2_merge_b, dim3(cdiv(maxq, 128), 1, n), dim3(128), 0, st, b, nsplit);
+        OVO_LAUNCH_CHECK();
+    }
+    OVO_LAUNCH(k_match_gather_b, dim3(n), dim3(1024), 0, st, gp, b);
+    OVO_LAUNCH_CHECK();
+    OVO_LAUNCH(k_umeyama_b, dim3(n), dim3(256), 0, st, b, cap);
+    OVO_LAUNCH_CHECK();
+    return 0;
+}
+int pair_item_size() { return (int)sizeof(PairItem); }
+int pair_max_batch() { return kMaxPairs; }
 
 int match_gather_launch(const GatherParams& p, const int32_t* nn, int nq, const float* kp1, const float* kp2, const float* disp1,
                         const float* disp2, int32_t* matches_out, float* pts1, float* pts2, int32_t* counts_out, cudaStream_t st) {

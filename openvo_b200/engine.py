@@ -151,6 +151,18 @@ class Engine:
         N.check(self.lib, self.lib.ovo_rigid_transform(self.ctx, self.pts1[slot].data_ptr(), self.pts2[slot].data_ptr(), counts_ptr,
                                                        self.kp_cap, out.data_ptr(), st))
 
+    def pair_batch_async(self, jobs, match_threshold):
+        """jobs: list of (frame a, frame b, slot).  All pairs in four launches (ovo_pair_batch); results land in pair_out[slot]."""
+        if not jobs:
+            return
+        items = (N.PairItem * len(jobs))()
+        for it, (a, b, slot) in zip(items, jobs):
+            it.q_desc, it.t_desc, it.nq, it.nt = a.desc.data_ptr(), b.desc.data_ptr(), a.n_kp, b.n_kp
+            it.kp1, it.kp2, it.disp1, it.disp2 = a.kp.data_ptr(), b.kp.data_ptr(), a.disp.data_ptr(), b.disp.data_ptr()
+            it.nn, it.matches = self.nn[slot].data_ptr(), self.matches[slot].data_ptr()
+            it.pts1, it.pts2, it.out = self.pts1[slot].data_ptr(), self.pts2[slot].data_ptr(), self.pair_out[slot].data_ptr()
+        N.check(self.lib, self.lib.ovo_pair_batch(self.ctx, len(jobs), items, float(match_threshold), self._stream()))
+
     def pair_collect(self, nslots=1):
         """One D2H (144 bytes per slot) + one stream sync -> list of (n_matches, n_bad_lookups, out16 numpy)."""
         self.pair_host[:nslots].copy_(self.pair_out[:nslots], non_blocking=True)

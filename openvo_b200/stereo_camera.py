@@ -68,9 +68,9 @@ class StereoCamera:
         self._engines = {}
 
     # ---- device engine (one per (nfeatures, batch, mask range)) -------------------------------------------------------
-    def engine(self, nfeatures=500, max_batch=1, min_valid=4.0, max_valid=100.0, lib_path=None):
+    def engine(self, nfeatures=500, max_batch=1, min_valid=4.0, max_valid=100.0, lib_path=None, tag=0):
         from .engine import Engine
-        key = (int(nfeatures), int(max_batch), float(min_valid), float(max_valid))
+        key = (int(nfeatures), int(max_batch), float(min_valid), float(max_valid), tag)
         eng = self._engines.get(key)
         if eng is None:
             eng = Engine(self.img_size[0], self.img_size[1], self.sgbm_params, self.valid_region_left, self.Q, nfeatures,

@@ -78,10 +78,11 @@ class StereoOdometer:
     MAX_ROTATION_CHANGE = np.pi / 3
 
     def __init__(self, stereo_camera, nfeatures=500, match_threshold=0.8, rigidity_threshold=0, outlier_threshold=0,
-                 preprocessed_frames=False, min_matches=10, _max_batch=1):
+                 preprocessed_frames=False, min_matches=10, _max_batch=1, _engine_tag=0):
         self.stereo = stereo_camera
         self._nfeatures = nfeatures
         self._max_batch = _max_batch  # >1 only when driven by openvo_b200.batch.BatchOdometer
+        self._engine_tag = _engine_tag
         self._cur = None   # last committed frame (device resident)
         self._prev = None  # the one before
         self.orb, self.matcher = _OrbHandle(self), _MatcherHandle(self)
@@ -96,7 +97,7 @@ class StereoOdometer:
         self.last_T = None
 
     def _engine(self):
-        return self.stereo.engine(self._nfeatures, self._max_batch, float(self.MIN_VALID_DISPARITY), float(self.MAX_VALID_DISPARITY))
+        return self.stereo.engine(self._nfeatures, self._max_batch, float(self.MIN_VALID_DISPARITY), float(self.MAX_VALID_DISPARITY), tag=self._engine_tag)
 
     # ---- lazily materialised public state (reference types) --------------------------------------------------------------
     def _host(self, frame, what):

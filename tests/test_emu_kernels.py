@@ -126,6 +126,35 @@ def test_match_and_pose_kernels(emu):
             b = O.bilinear_lookup(ref3, float(kp2[nn[i, 0], 0]), float(kp2[nn[i, 0], 1]))
             assert np.array_equal(a.view(np.uint32), p1[j].view(np.uint32)) or np.isnan(a).any()
             assert np.array_equal(b.view(np.uint32), p2[j].view(np.uint32)) or np.isnan(b).any()
+    # batched pair step (ovo_pair_batch) == the three single-pair seams
+    items = (N.PairItem * 2)()
+    outs, keepers = [], []
+    for j, (qq, tt, ka, kb) in enumerate(((q, t, kp1, kp2), (t[:150], q, kp2[:150], kp1))):
+        bufs = dict(q=np.ascontiguousarray(qq), t=np.ascontiguousarray(tt), ka=np.ascontiguousarray(ka), kb=np.ascontiguousarray(kb),
+                    nn=np.zeros((len(qq), 4), np.int32), m=np.zeros((len(qq), 3), np.int32), p1=np.zeros((len(qq), 3), np.float32),
+                    p2=np.zeros((len(qq), 3), np.float32), out=np.zeros(18))
+        keepers.append(bufs)
+        it = items[j]
+        it.q_desc, it.t_desc, it.nq, it.nt = N.ptr(bufs["q"]), N.ptr(bufs["t"]), len(qq), len(tt)
+        it.kp1, it.kp2, it.disp1, it.disp2 = N.ptr(bufs["ka"]), N.ptr(bufs["kb"]), N.ptr(df), N.ptr(df)
+        it.nn, it.matches, it.pts1, it.pts2, it.out = N.ptr(bufs["nn"]), N.ptr(bufs["m"]), N.ptr(bufs["p1"]), N.ptr(bufs["p2"]), N.ptr(bufs["out"])
+    c2 = Ctx(emu, W, H, sgbm_params(32), roi, Q, n, nb=2)
+    N.check(emu, emu.ovo_pair_batch(c2.ctx, 2, items, 0.8, None))
+    for bufs in keepers:
+        qq, tt = bufs["q"], bufs["t"]
+        nn1 = np.zeros((len(qq), 4), np.int32)
+        N.check(emu, emu.ovo_knn2_hamming(c.ctx, N.ptr(qq), len(qq), N.ptr(tt), len(tt), N.ptr(nn1), None))
+        assert np.array_equal(nn1, bufs["nn"])
+        m1, a1, b1, c1 = np.zeros((len(qq), 3), np.int32), np.zeros((len(qq), 3), np.float32), np.zeros((len(qq), 3), np.float32), np.zeros(2, np.int32)
+        N.check(emu, emu.ovo_match_points(c.ctx, N.ptr(nn1), len(qq), 0.8, N.ptr(bufs["ka"]), N.ptr(bufs["kb"]), N.ptr(df), N.ptr(df),
+                                         N.ptr(m1), N.ptr(a1), N.ptr(b1), N.ptr(c1), None))
+        cnt_b = bufs["out"][16:17].view(np.int32)
+        assert cnt_b[0] == c1[0] and cnt_b[1] == c1[1]
+        k = c1[0]
+        assert np.array_equal(m1[:k], bufs["m"][:k]) and np.array_equal(a1[:k].view(np.uint32), bufs["p1"][:k].view(np.uint32))
+        o1 = np.zeros(16)
+        N.check(emu, emu.ovo_rigid_transform(c.ctx, N.ptr(a1), N.ptr(b1), N.ptr(c1), c.cap, N.ptr(o1), None))
+        assert np.array_equal(o1, bufs["out"][:16], equal_nan=True)
     # Umeyama
     src = rng.normal(0, 5, (150, 3)).astype(np.float32)
     ang = 0.04
