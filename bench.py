@@ -169,7 +169,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="K", choices=list(CONFIGS))
-    ap.add_argument("--seqs", type=int, default=8, help="independent sequences (= frames per step) per GPU")
+    ap.add_argument("--seqs", type=int, default=16, help="independent sequences (= frames per step) per GPU")
     ap.add_argument("--threads", type=int, default=2, help="host threads (each with its own CUDA stream and share of the sequences)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--_cpu_worker", nargs=5, default=None)

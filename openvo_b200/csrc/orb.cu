@@ -100,6 +100,16 @@ __global__ void __launch_bounds__(kFastTX* kFastTY) k_orb_fast(OrbDims d, OrbWor
     if (x >= 3 && x < L.w - 3 && y >= 3 && y < L.h - 3) {
         const int cx = threadIdx.x + 3, cy = threadIdx.y + 3;
         const int c = tile[cy][cx];
+        // any 9-arc of the ring covers at least two of the four compass pixels
+        {
+            const int a0 = c - tile[cy + 3][cx], a4 = c - tile[cy][cx + 3], a8 = c - tile[cy - 3][cx], a12 = c - tile[cy][cx - 3];
+            const int nb = (a0 > kFastT) + (a4 > kFastT) + (a8 > kFastT) + (a12 > kFastT);
+            const int nd = (a0 < -kFastT) + (a4 < -kFastT) + (a8 < -kFastT) + (a12 < -kFastT);
+            if (nb < 2 && nd < 2) {
+                fptr(ws.score, ws_stride, f)[L.off + (size_t)y * L.w + x] = 0;
+                return;
+            }
+        }
         int v[16];
         v[0] = c - tile[cy + 3][cx];      v[1] = c - tile[cy + 3][cx + 1];  v[2] = c - tile[cy + 2][cx + 2];  v[3] = c - tile[cy + 1][cx + 3];
         v[4] = c - tile[cy][cx + 3];      v[5] = c - tile[cy - 1][cx + 3];  v[6] = c - tile[cy - 2][cx + 2];  v[7] = c - tile[cy - 3][cx + 1];
@@ -353,6 +363,10 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 
 __global__ void __launch_bounds__(128) k_orb_describe(OrbDims d, OrbWorkspace ws, size_t ws_stride, const int32_t* __restrict__ n_sel,
                                                       float* __restrict__ kp_out, uint8_t* __restrict__ desc_out) {
+    // the sampling pattern is indexed per lane: constant memory would serialise the 32 different addresses
+    __shared__ signed char s_pattern[1024];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_pattern[i] = c_pattern[i];
+    __syncthreads();
     const int f = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -396,7 +410,7 @@ __global__ void __launch_bounds__(128) k_orb_describe(OrbDims d, OrbWorkspace ws
     uint32_t byte = 0;
 #pragma unroll
     for (int b = 0; b < 8; b++) {
-        const signed char* q = c_pattern + (lane * 8 + b) * 4;
+        const signed char* q = s_pattern + (lane * 8 + b) * 4;
         int val[2];
 #pragma unroll
         for (int e = 0; e < 2; e++) {

@@ -317,8 +317,10 @@ __device__ __forceinline__ void vert_line(const SgbmDims& d, const uint32_t* __r
 template <int NPR, bool PAD>
 __global__ void __launch_bounds__(256) k_sgbm_vert(SgbmDims d, SgbmWorkspace ws, size_t ws_stride) {
     const int lane = threadIdx.x & 31;
-    const int line = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int dir = blockIdx.y, f = blockIdx.z;
+    // direction is the fastest-varying block coordinate: the three directions of the same columns are resident together and
+    // share their reads of C through L2
+    const int dir = blockIdx.x % 3, f = blockIdx.y;
+    const int line = (blockIdx.x / 3) * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (line >= d.W1) return;
     const uint32_t* C = reinterpret_cast<const uint32_t*>(frame_ptr(ws.C, ws_stride, f)) + lane * NPR;
     uint32_t* Lout = reinterpret_cast<uint32_t*>(frame_ptr(ws.Lv, ws_stride, f)) + (size_t)dir * d.H * d.W1 * (32 * NPR) + lane * NPR;
@@ -658,7 +660,7 @@ __global__ void k_ccl_apply(const int16_t* __restrict__ img, const int32_t* __re
 
 template <int NPR, bool PAD>
 int launch_paths(const SgbmDims& d, const SgbmWorkspace& ws, size_t ws_stride, int nb, cudaStream_t st) {
-    dim3 gv(cdiv(d.W1, 8), 3, nb);
+    dim3 gv(3 * cdiv(d.W1, 8), nb);
     { auto k_sgbm_vert_t = k_sgbm_vert<NPR, PAD>; OVO_LAUNCH(k_sgbm_vert_t, gv, dim3(256), 0, st, d, ws, ws_stride); }
     OVO_LAUNCH_CHECK();
     dim3 gh(d.H, nb);

@@ -1,0 +1,34 @@
+"""Summarise an `ncu --page raw --csv` dump into the handful of metrics DESIGN.md / profiles/ quote."""
+import csv
+import sys
+
+WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "smsp__inst_executed.sum",
+        "lts__t_sector_hit_rate.pct", "launch__grid_size", "launch__block_size", "launch__waves_per_multiprocessor",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio"]
+
+
+def main(path):
+    rows = list(csv.reader(open(path)))
+    H, U = rows[0], rows[1]
+    ki = H.index("Kernel Name")
+    for r in rows[2:]:
+        print("## " + r[ki].split("(")[0])
+        for w in WANT:
+            if w in H:
+                print("  %-80s %s %s" % (w, r[H.index(w)], U[H.index(w)]))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])
