@@ -315,7 +315,9 @@ def main():
     if rank == 0:
         bos = dev["bos"]
         lib.ovo_profile_enable(1)
-        run(bos, min(a.steps, 5), warmup + a.steps, False)
+        with torch.cuda.stream(streams[0]):  # one stream only: event pairs around each launch must not see the other stream's kernels
+            run_part(bos[0], 0, min(a.steps, 5), warmup + a.steps, False)
+        torch.cuda.synchronize()
         prof = _native.profile_read(lib)
         lib.ovo_profile_enable(0)
         tot = sum(v[0] for v in prof.values()) or 1.0
@@ -338,6 +340,40 @@ def main():
         roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": which, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": abytes,
                     "ms_per_launch": dur_s * 1e3, "share_of_step": prof[top][0] / tot}
+    stages = None
+    if rank == 0 and per_kernel:
+        # per-stage view (SURVEY.md §8(d) contract numerators); times are per frame from the single-stream event profile
+        def t_of(prefixes):
+            return sum(v["ms_per_launch"] * v["launches"] for k, v in per_kernel.items() if k.startswith(prefixes)) / (min(a.steps, 5) * SP)
+        W_, H_, D_ = cfg["W"], cfg["H"], cfg["D"]
+        eng0 = dev["bos"][0].engine
+        nkp = float(np.mean([od._cur.n_kp for b in dev["bos"] for od in b.odometers if od._cur is not None] or [0]))
+        ipk = {}
+        try:
+            ipk = json.load(open(os.path.join(ROOT, "profiles", "int_peaks.json")))
+        except Exception:
+            pass
+        t4 = t_of(("k_sgbm", "k_median3", "k_ccl"))
+        t12 = t_of(("k_orb",))
+        t3 = t_of(("k_knn2",))
+        t5 = t_of(("k_match_gather", "k_umeyama"))
+        ops4 = 76.0 * (W_ - D_) * H_ * D_
+        bytes12 = 19.5 * eng0.cw * eng0.ch + 1400.0 * nkp
+        ops3 = 27.0 * nkp * nkp
+        int_peak = ipk.get("int32_add_logic_gops")
+        popc_peak = ipk.get("popc_xor_add_gops")
+        stages = {
+            "stage4_sgbm": {"ms_per_frame": t4, "int_ops_per_frame": ops4, "achieved_gops": ops4 / (t4 * 1e-3) / 1e9 if t4 else None,
+                            "peak_gops": int_peak, "frac": (ops4 / (t4 * 1e-3) / 1e9 / int_peak) if (t4 and int_peak) else None,
+                            "peak_source": "profiles/int_peaks.json int32_add_logic (measured, tools/int_peak.cu)"},
+            "stage12_orb": {"ms_per_frame": t12, "bytes_per_frame": bytes12, "achieved_gbs": bytes12 / (t12 * 1e-3) / 1e9 if t12 else None,
+                            "peak_gbs": peak, "frac": (bytes12 / (t12 * 1e-3) / 1e9 / peak) if t12 else None, "keypoints": nkp,
+                            "note": "device kernels only; the retainBest host step is outside"},
+            "stage3_match": {"ms_per_frame": t3, "int_ops_per_frame": ops3, "achieved_gops": ops3 / (t3 * 1e-3) / 1e9 if t3 else None,
+                             "peak_gops": popc_peak, "frac": (ops3 / (t3 * 1e-3) / 1e9 / popc_peak) if (t3 and popc_peak) else None,
+                             "peak_source": "profiles/int_peaks.json popc_xor_add (measured)"},
+            "stage5_pose": {"ms_per_frame": t5, "note": "latency-bound; no roofline (SURVEY.md §8(d))"},
+        }
     if rank == 0:
         line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": a.steps, "warmup": warmup,
                 "ms_per_step": dev["ms"] / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i16",
@@ -348,7 +384,7 @@ def main():
                 "clocks": dev["clocks"], "gpu_launches": dev["launches"],
                 "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                         "ms_per_step": e2e["ms"] / a.steps},
-                "roofline": roofline, "kernels": per_kernel}
+                "roofline": roofline, "stages": stages, "kernels": per_kernel}
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line))

@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libopenvo_b200.so")
+LIB_PATH = os.environ.get("OVO_B200_LIB") or os.path.join(_HERE, "lib", "libopenvo_b200.so")  # env override: kernel-variant experiments
 
 SGBM_KEYS = ("minDisparity", "numDisparities", "blockSize", "P1", "P2", "disp12MaxDiff", "preFilterCap",
              "uniquenessRatio", "speckleWindowSize", "speckleRange")

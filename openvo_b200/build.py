@@ -17,6 +17,24 @@ def _stale(out, deps):
     return not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps)
 
 
+def build_variant(name, defines):
+    """Experiment helper: a separately named library with extra -D flags (openvo_b200/lib/variants/<name>.so)."""
+    vdir = os.path.join(LIBDIR, "variants")
+    os.makedirs(vdir, exist_ok=True)
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    objs = []
+    for f in CU + CPP:
+        obj = os.path.join(vdir, name + "_" + f + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-x", "cu"] if f.endswith(".cpp") else []) + ["-c", os.path.join(CSRC, f), "-o", obj]
+        subprocess.run(cmd, capture_output=True, text=True, check=True)
+        objs.append(obj)
+    out = os.path.join(vdir, name + ".so")
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + objs + ["-lcudart"])
+    for o in objs:
+        os.remove(o)
+    return out
+
+
 def build(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".inc", ".h"))]

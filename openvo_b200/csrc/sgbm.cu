@@ -335,7 +335,16 @@ __global__ void __launch_bounds__(256) k_sgbm_vert(SgbmDims d, SgbmWorkspace ws,
 // warp reads the other's T, adds its own path and owns the complete S for the cell.  disp2 is order-independent:
 // min cost, ties to the larger x (= larger d), which is what the reference's right-to-left sweep keeps.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kHorPF = 4;
+#ifndef OVO_HOR_PF1
+#define OVO_HOR_PF1 4
+#endif
+#ifndef OVO_HOR_PF2
+#define OVO_HOR_PF2 4
+#endif
+#ifndef OVO_HOR_MINB
+#define OVO_HOR_MINB 1
+#endif
+constexpr int kHorPF1 = OVO_HOR_PF1, kHorPF2 = OVO_HOR_PF2;  // register prefetch depth (cells) of the two phases
 
 template <int NPR>
 __device__ __forceinline__ uint32_t half_of(const uint32_t (&S)[NPR], int k) {  // k = 2*r + h, compile-time after unrolling
@@ -393,7 +402,7 @@ __device__ __forceinline__ void wta_cell(const uint32_t (&S)[NPR], int lane, con
 }
 
 template <int NPR, bool PAD>
-__global__ void __launch_bounds__(64) k_sgbm_horiz(SgbmDims d, SgbmWorkspace ws, size_t ws_stride) {
+__global__ void __launch_bounds__(64, OVO_HOR_MINB) k_sgbm_horiz(SgbmDims d, SgbmWorkspace ws, size_t ws_stride) {
     OVO_DYN_SMEM(uint32_t, hsm);
     uint32_t* d2key = hsm;                                        // [W]
     uint32_t* selA = hsm + d.W;                                   // [W1] minS | runner-up << 16
@@ -432,12 +441,12 @@ __global__ void __launch_bounds__(64) k_sgbm_horiz(SgbmDims d, SgbmWorkspace ws,
     path_reset<NPR>(s);
     // ---- phase 1: T = sat(L1 + L2 + L3 + own)
     {
-        uint32_t cb[kHorPF][NPR], l1[kHorPF][NPR], l2[kHorPF][NPR], l3[kHorPF][NPR];
+        uint32_t cb[kHorPF1][NPR], l1[kHorPF1][NPR], l2[kHorPF1][NPR], l3[kHorPF1][NPR];
         const uint32_t *pc = C + xa * WPC, *p1 = L1 + xa * WPC, *p3 = L3 + xa * WPC;
         const uint32_t* p2 = T + xa * WPC;
         uint32_t* po = T + xa * WPC;
 #pragma unroll
-        for (int i = 0; i < kHorPF; i++) {
+        for (int i = 0; i < kHorPF1; i++) {
             if (i < n1) { ldv<NPR>(cb[i], pc); ldv<NPR>(l1[i], p1); ldv<NPR>(l2[i], p2); ldv<NPR>(l3[i], p3); }
             pc += dstep; p1 += dstep; p2 += dstep; p3 += dstep;
         }
@@ -457,24 +466,24 @@ __global__ void __launch_bounds__(64) k_sgbm_horiz(SgbmDims d, SgbmWorkspace ws,
             po += dstep;
         };
         int k = 0;
-        for (; k + 2 * kHorPF <= n1; k += kHorPF) {
+        for (; k + 2 * kHorPF1 <= n1; k += kHorPF1) {
 #pragma unroll
-            for (int i = 0; i < kHorPF; i++) body(i, true);
+            for (int i = 0; i < kHorPF1; i++) body(i, true);
         }
-        for (; k < n1; k += kHorPF) {
+        for (; k < n1; k += kHorPF1) {
 #pragma unroll
-            for (int i = 0; i < kHorPF; i++)
-                if (k + i < n1) body(i, k + i + kHorPF < n1);
+            for (int i = 0; i < kHorPF1; i++)
+                if (k + i < n1) body(i, k + i + kHorPF1 < n1);
         }
     }
     __syncthreads();
     // ---- phase 2: S = sat(T_other + own) -> selection
     {
         const int xb = xa + dirx * n1;
-        uint32_t cb[kHorPF][NPR], tb[kHorPF][NPR];
+        uint32_t cb[kHorPF2][NPR], tb[kHorPF2][NPR];
         const uint32_t *pc = C + xb * WPC, *pt = T + xb * WPC;
 #pragma unroll
-        for (int i = 0; i < kHorPF; i++) {
+        for (int i = 0; i < kHorPF2; i++) {
             if (i < n2) { ldv<NPR>(cb[i], pc); ldv<NPR>(tb[i], pt); }
             pc += dstep; pt += dstep;
         }
@@ -493,14 +502,14 @@ __global__ void __launch_bounds__(64) k_sgbm_horiz(SgbmDims d, SgbmWorkspace ws,
             x1 += dirx;
         };
         int k = 0;
-        for (; k + 2 * kHorPF <= n2; k += kHorPF) {
+        for (; k + 2 * kHorPF2 <= n2; k += kHorPF2) {
 #pragma unroll
-            for (int i = 0; i < kHorPF; i++) body(i, true);
+            for (int i = 0; i < kHorPF2; i++) body(i, true);
         }
-        for (; k < n2; k += kHorPF) {
+        for (; k < n2; k += kHorPF2) {
 #pragma unroll
-            for (int i = 0; i < kHorPF; i++)
-                if (k + i < n2) body(i, k + i + kHorPF < n2);
+            for (int i = 0; i < kHorPF2; i++)
+                if (k + i < n2) body(i, k + i + kHorPF2 < n2);
         }
     }
     __syncthreads();
