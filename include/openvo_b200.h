@@ -64,6 +64,13 @@ void ovo_destroy(ovo_ctx* ctx);
 int ovo_sgbm_compute(ovo_ctx* ctx, const uint8_t* left_dev, const uint8_t* right_dev, int pitch, size_t frame_stride,
                      int nb, int16_t* disp_dev, void* stream);
 
+/* §8(f) n1 + n2 — replaces cv2.cvtColor(img, COLOR_BGR2GRAY) and cv2.remap(img, map_1, map_2, INTER_LINEAR)
+ * (ref: src/openVO/stereo_camera.py:44-50, 29-33).  img: u8 [nb][height][pitch], `channels` = 1 (gray) or 3 (BGR, converted per
+ * tap with OpenCV's 15-bit coefficients).  map1: i16 [height][width][2] (CV_16SC2), map2: u16 [height][width] as produced by
+ * cv2.initUndistortRectifyMap(..., CV_16SC2); pass both NULL for colour conversion only.  out: u8 [nb][height][width]. */
+int ovo_rectify(ovo_ctx* ctx, const uint8_t* img_dev, int channels, int pitch, size_t frame_stride, int nb, const int16_t* map1_dev,
+                const uint16_t* map2_dev, uint8_t* out_dev, void* stream);
+
 /* a2 + a4 + a5 — replaces `.astype(np.float32)/16`, the crop and StereoOdometer.feature_mask
  * (ref: src/openVO/stereo_camera.py:51,54; src/openVO/stereo_odometer.py:38-41).
  * disp: i16 [nb][height][width] -> disp_f32: f32 [nb][ch][cw], mask: u8 [nb][ch][cw] (0 / 255). */

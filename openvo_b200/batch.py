@@ -16,9 +16,11 @@ class BatchOdometer:
         self.engine = self.odometers[0]._engine()
 
     def update(self, lefts, rights):
-        """lefts/rights: numpy uint8 [S,H,W] host frames (rectified, gray) -> list of S bools."""
+        """lefts/rights: numpy uint8 host frames [S,H,W] (gray) or [S,H,W,3] (BGR); rectified on the device unless the
+        odometers were built with preprocessed_frames=True -> list of S bools."""
         eng = self.engine
-        return self.update_device(eng.upload(np.asarray(lefts), "b_l"), eng.upload(np.asarray(rights), "b_r"))
+        l, r = self.stereo._prepare_device(eng, lefts, rights, self.odometers[0].preprocessed_frames, key="b")
+        return self.update_device(l, r)
 
     def update_device(self, lefts, rights):
         """Same, with the frames already resident on the device (torch uint8 [S,H,W])."""

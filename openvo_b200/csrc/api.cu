@@ -60,6 +60,8 @@ int disp_post_launch(const int16_t* disp, int W, int H, int x0, int y0, int cw, 
                      uint8_t* mask, int nb, cudaStream_t st);
 int pair_batch_launch(const GatherParams& gp, int n, const void* items_host, int cap, cudaStream_t st);
 int pair_item_size();
+int rectify_launch(const uint8_t* img, int pitch, size_t frame_stride, int ch, int W, int H, int nb, const int16_t* map1,
+                   const uint16_t* map2, uint8_t* out, cudaStream_t st);
 int pair_max_batch();
 int crop_launch(const uint8_t* img, int pitch, size_t frame_stride, int x0, int y0, int cw, int ch, int nb, uint8_t* out, cudaStream_t st);
 
@@ -268,6 +270,15 @@ int ovo_disparity_post(ovo_ctx* c, const int16_t* disp, int nb, float* disp_f32,
 int ovo_crop_left(ovo_ctx* c, const uint8_t* img, int pitch, size_t frame_stride, int nb, uint8_t* out, void* stream) {
     CHECK_CTX(c, nb);
     return crop_launch(img, pitch, frame_stride, c->L.x0, c->L.y0, c->L.cw, c->L.ch, nb, out, (cudaStream_t)stream);
+}
+
+int ovo_rectify(ovo_ctx* c, const uint8_t* img, int channels, int pitch, size_t frame_stride, int nb, const int16_t* map1,
+                const uint16_t* map2, uint8_t* out, void* stream) {
+    CHECK_CTX(c, nb);
+    if (channels != 1 && channels != 3) { set_error("channels must be 1 (gray) or 3 (BGR)"); return 1; }
+    if ((map1 == nullptr) != (map2 == nullptr)) { set_error("map1 and map2 must both be given or both be NULL"); return 1; }
+    if (pitch < c->L.sg.W * channels) { set_error("pitch < width*channels"); return 1; }
+    return rectify_launch(img, pitch, frame_stride, channels, c->L.sg.W, c->L.sg.H, nb, map1, map2, out, (cudaStream_t)stream);
 }
 
 int ovo_reproject_3d(ovo_ctx* c, const float* disp_f32, float* xyz, void* stream) {

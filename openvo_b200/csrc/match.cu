@@ -428,7 +428,45 @@ __global__ void k_crop_u8(const uint8_t* __restrict__ img, int pitch, size_t fra
     out[((size_t)f * ch + y) * cw + x] = img[frame_stride * f + (size_t)(y + y0) * pitch + x + x0];
 }
 
+// ---- rectification (SURVEY.md §8(f) n1 + n2) -----------------------------------------------------------------------------------
+// cv2.remap(img, map1 (int16 x,y), map2 (uint16 = fy*32 + fx), INTER_LINEAR), BORDER_CONSTANT 0, with cv2.cvtColor(BGR2GRAY)
+// fused in for 3-channel input (the reference converts first, ref: src/openVO/stereo_camera.py:44-50; per-tap conversion is the
+// same arithmetic).  Weights are exact integers: (32-fx)(32-fy)*32 etc., sum 32768; dst = (sum + 2^14) >> 15.
+__device__ __forceinline__ int gray_at(const uint8_t* __restrict__ img, int pitch, int ch, int x, int y) {
+    const uint8_t* p = img + (size_t)y * pitch + (size_t)x * ch;
+    if (ch == 1) return p[0];
+    return (3735 * (int)p[0] + 19235 * (int)p[1] + 9798 * (int)p[2] + (1 << 14)) >> 15;
+}
+
+__global__ void k_rectify(const uint8_t* __restrict__ img, int pitch, size_t frame_stride, int ch, int W, int H,
+                          const int16_t* __restrict__ map1, const uint16_t* __restrict__ map2, uint8_t* __restrict__ out) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
+    if (x >= W) return;
+    const uint8_t* I = img + frame_stride * f;
+    int v;
+    if (map1 == nullptr) {
+        v = gray_at(I, pitch, ch, x, y);  // colour conversion only
+    } else {
+        const int sx = map1[2 * ((size_t)y * W + x)], sy = map1[2 * ((size_t)y * W + x) + 1];
+        const int m = map2[(size_t)y * W + x];
+        const int fx = m & 31, fy = (m >> 5) & 31;
+        auto tap = [&](int xx, int yy) -> int { return (xx >= 0 && xx < W && yy >= 0 && yy < H) ? gray_at(I, pitch, ch, xx, yy) : 0; };
+        const int acc = tap(sx, sy) * ((32 - fx) * (32 - fy) * 32) + tap(sx + 1, sy) * (fx * (32 - fy) * 32) +
+                        tap(sx, sy + 1) * ((32 - fx) * fy * 32) + tap(sx + 1, sy + 1) * (fx * fy * 32);
+        v = (acc + (1 << 14)) >> 15;
+    }
+    out[((size_t)f * H + y) * W + x] = (uint8_t)v;
+}
+
 }  // namespace
+
+int rectify_launch(const uint8_t* img, int pitch, size_t frame_stride, int ch, int W, int H, int nb, const int16_t* map1,
+                   const uint16_t* map2, uint8_t* out, cudaStream_t st) {
+    dim3 grid(cdiv(W, 128), H, nb);
+    OVO_LAUNCH(k_rectify, grid, dim3(128), 0, st, img, pitch, frame_stride, ch, W, H, map1, map2, out);
+    OVO_LAUNCH_CHECK();
+    return 0;
+}
 
 size_t knn2_scratch_bytes(int nq_cap, int nt_cap) { return (size_t)nq_cap * 32 * 2 * 4; }
 

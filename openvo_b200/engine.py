@@ -117,6 +117,25 @@ class Engine:
         N.check(self.lib, self.lib.ovo_crop_left(self.ctx, img.data_ptr(), self.W, self.W * self.H, nb, out.data_ptr(), self._stream()))
         return out
 
+    def rectify(self, img, maps=None):
+        """img: device u8 [nb,H,W] (gray) or [nb,H,W,3] (BGR); maps: (map1 i16 [H,W,2], map2 u16 [H,W]) device tensors or None
+        (colour conversion only) -> device u8 [nb,H,W] (cv2.cvtColor + cv2.remap seams)."""
+        nb = img.shape[0]
+        ch = 3 if img.dim() == 4 else 1
+        out = torch.empty((nb, self.H, self.W), dtype=torch.uint8, device=self.device)
+        m1, m2 = (maps[0].data_ptr(), maps[1].data_ptr()) if maps is not None else (None, None)
+        N.check(self.lib, self.lib.ovo_rectify(self.ctx, img.data_ptr(), ch, self.W * ch, self.W * self.H * ch, nb, m1, m2,
+                                               out.data_ptr(), self._stream()))
+        return out
+
+    def device_maps(self, key, map1, map2):
+        """Upload (once) a CV_16SC2 rectification map pair."""
+        cache = self.__dict__.setdefault("_maps", {})
+        if key not in cache:
+            cache[key] = (torch.from_numpy(np.ascontiguousarray(map1, np.int16)).to(self.device),
+                          torch.from_numpy(np.ascontiguousarray(map2).view(np.int16).astype(np.int16)).to(self.device))
+        return cache[key]
+
     def reproject(self, disp_f32):
         xyz = torch.empty((self.ch, self.cw, 3), dtype=torch.float32, device=self.device)
         N.check(self.lib, self.lib.ovo_reproject_3d(self.ctx, disp_f32.data_ptr(), xyz.data_ptr(), self._stream()))

@@ -80,15 +80,25 @@ class StereoCamera:
 
     # ---- reference API ---------------------------------------------------------------------------------------------------
     def undistort_rectify_left(self, img):
-        return self._remap(img, self.map_left_1, self.map_left_2)
+        # ref: src/openVO/stereo_camera.py:29-30 (cv2.remap on the device)
+        return self._rectify_host(img, "left")
 
     def undistort_rectify_right(self, img):
-        return self._remap(img, self.map_right_1, self.map_right_2)
+        # ref: src/openVO/stereo_camera.py:32-33
+        return self._rectify_host(img, "right")
 
-    def _remap(self, img, map1, map2):
-        raise NotImplementedError(
-            "openvo_b200: cv2.remap rectification (ref: src/openVO/stereo_camera.py:29-33) is a SURVEY.md §8(f) 'next' row "
-            "and is not on the device yet; pass rectified frames with preprocessed=True / preprocessed_frames=True")
+    def _maps(self, eng, side):
+        m = (self.map_left_1, self.map_left_2) if side == "left" else (self.map_right_1, self.map_right_2)
+        return eng.device_maps(side, m[0], m[1])
+
+    def _rectify_host(self, img, side):
+        img = np.asarray(img)
+        self._check(img)
+        if img.ndim == 3:
+            raise ValueError("cv2.remap keeps the channel count; the hot path only rectifies single-channel images "
+                             "(compute_3d converts colour input to gray first, like the reference)")
+        eng = self.engine()
+        return eng.rectify(eng.upload(img[None], "rect_" + side), self._maps(eng, side))[0].cpu().numpy()
 
     def crop_to_valid_region_left(self, img):
         r = self.valid_region_left
@@ -98,30 +108,34 @@ class StereoCamera:
         r = self.valid_region_right
         return img[r[1]:r[3], r[0]:r[2]]
 
-    def _gray(self, img):
-        img = np.asarray(img)
-        if img.ndim == 3:
-            raise NotImplementedError(
-                "openvo_b200: cv2.cvtColor(BGR2GRAY) (ref: src/openVO/stereo_camera.py:44-47) is a SURVEY.md §8(f) 'next' "
-                "row and is not on the device yet; pass grayscale frames")
-        return img
-
-    def _prepare(self, img_left, img_right, preprocessed):
-        img_left, img_right = self._gray(img_left), self._gray(img_right)
-        if not preprocessed:
-            img_left = self.undistort_rectify_left(img_left)
-            img_right = self.undistort_rectify_right(img_right)
-        if img_left.shape != img_right.shape or img_left.dtype != np.uint8 or img_right.dtype != np.uint8:
-            raise ValueError("left and right must be uint8 images of equal size (the reference raises cv2.error here)")
-        if img_left.shape != (self.img_size[1], self.img_size[0]):
+    def _check(self, img):
+        if img.dtype != np.uint8 or img.ndim not in (2, 3) or (img.ndim == 3 and img.shape[2] != 3):
+            raise ValueError("images must be uint8, HxW (gray) or HxWx3 (BGR) (the reference raises cv2.error here)")
+        if img.shape[:2] != (self.img_size[1], self.img_size[0]):
             raise ValueError("image size differs from the camera's img_size")
-        return img_left, img_right
+
+    def _prepare_device(self, eng, img_left, img_right, preprocessed, key="prep"):
+        """Host frames ([H,W] / [H,W,3], or batches [S,H,W] / [S,H,W,3]) -> rectified gray device tensors [S,H,W]
+        (ref: src/openVO/stereo_camera.py:44-50: cvtColor if colour, remap unless preprocessed — both on the device)."""
+        out = []
+        for side, img in (("left", img_left), ("right", img_right)):
+            img = np.asarray(img)
+            hw = (self.img_size[1], self.img_size[0])
+            if img.shape[:2] == hw and img.ndim in (2, 3):  # a single frame
+                img = img[None]
+            self._check(img[0])
+            dev = eng.upload(img, key + "_" + side)
+            if img.ndim == 4 or not preprocessed:
+                dev = eng.rectify(dev, None if preprocessed else self._maps(eng, side))
+            out.append(dev)
+        if out[0].shape != out[1].shape:
+            raise ValueError("left and right must be of equal size (the reference raises cv2.error here)")
+        return out[0], out[1]
 
     def compute_3d(self, img_left, img_right, preprocessed=False):
         """ref: src/openVO/stereo_camera.py:43-55 -> (img_3d f32 H'xW'x3, disparity f32 H'xW', img_left u8 H'xW')."""
-        img_left, img_right = self._prepare(img_left, img_right, preprocessed)
         eng = self.engine()
-        l, r = eng.upload(img_left[None], "c3d_l"), eng.upload(img_right[None], "c3d_r")
+        l, r = self._prepare_device(eng, img_left, img_right, preprocessed, key="c3d")
         disp, _ = eng.disparity_post(eng.sgbm(l, r))
         xyz = eng.reproject(disp[0])
-        return xyz.cpu().numpy(), disp[0].cpu().numpy(), self.crop_to_valid_region_left(img_left)
+        return xyz.cpu().numpy(), disp[0].cpu().numpy(), eng.crop(l)[0].cpu().numpy()

@@ -164,9 +164,9 @@ class StereoOdometer:
     # ---- the per-frame call --------------------------------------------------------------------------------------------------
     def update(self, img_left, img_right):
         """ref: src/openVO/stereo_odometer.py:115-160."""
-        left, right = self.stereo._prepare(img_left, img_right, self.preprocessed_frames)
         eng = self._engine()
-        frame = eng.frames(eng.upload(left[None], "upd_l"), eng.upload(right[None], "upd_r"))[0]
+        left, right = self.stereo._prepare_device(eng, img_left, img_right, self.preprocessed_frames, key="upd")
+        frame = eng.frames(left, right)[0]
         return self._advance(frame)
 
     def _advance(self, frame, first=None):

@@ -31,6 +31,29 @@ def camera_args(W, H, num_disparities):
                 img_size=(W, H))
 
 
+def camera_args_distorted(W, H, num_disparities):
+    """A rig with lens distortion, slightly different intrinsics and a small relative rotation: exercises cv2.remap
+    rectification (preprocessed_frames=False, the reference's default) and a non-trivial valid-pixel ROI (B1)."""
+    a = camera_args(W, H, num_disparities)
+    a["dist_left"] = np.array([-0.12, 0.03, 0.0008, -0.0006, 0.0])
+    a["dist_right"] = np.array([-0.10, 0.02, -0.0005, 0.0007, 0.0])
+    a["K_right"] = a["K_right"] + np.array([[2.0, 0, 1.5], [0, 2.0, -1.0], [0, 0, 0]])
+    ax = np.array([0.004, -0.006, 0.002])
+    th = np.linalg.norm(ax)
+    k = ax / th
+    Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    a["rect_params"] = {"R": np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx, "T": np.array([-BASELINE_M, 0.002, 0.001])}
+    return a
+
+
+def to_bgr(gray, seed=0):
+    """A colour image whose cv2 BGR2GRAY conversion is close to `gray` (channels differ by small seeded offsets)."""
+    rng = np.random.default_rng(seed)
+    g = gray.astype(np.int16)
+    off = rng.integers(-12, 13, gray.shape + (3,))
+    return np.clip(g[..., None] + off, 0, 255).astype(np.uint8)
+
+
 def _texture(rng, n=2048, blk=4):
     t = rng.integers(0, 256, (n // blk, n // blk)).astype(np.float32)
     tex = np.kron(t, np.ones((blk, blk), np.float32)) * 0.75 + rng.integers(0, 64, (n, n)).astype(np.float32)

@@ -166,3 +166,23 @@ def test_match_and_pose_kernels(emu):
     T, s = O.umeyama(src, dst)
     assert np.abs(out[:12].reshape(3, 4) - T).max() < 1e-12 and abs(out[12] - s) < 1e-12
     assert abs(out[13] - O.rotation_angle(T[:, :3])) < 1e-10 and abs(out[14] - np.linalg.norm(T[:, 3])) < 1e-12
+
+
+def test_rectify_kernel(emu):
+    rng = np.random.default_rng(9)
+    W, H = 200, 120
+    c = Ctx(emu, W, H, sgbm_params(32), (0, 0, W, H), np.eye(4), 100, nb=2)
+    gray = rng.integers(0, 256, (2, H, W), dtype=np.uint8)
+    bgr = rng.integers(0, 256, (2, H, W, 3), dtype=np.uint8)
+    m1 = np.stack([rng.integers(-3, W + 3, (H, W)), rng.integers(-3, H + 3, (H, W))], -1).astype(np.int16)
+    m2 = rng.integers(0, 1024, (H, W)).astype(np.uint16)
+    out = np.zeros((2, H, W), np.uint8)
+    N.check(emu, emu.ovo_rectify(c.ctx, N.ptr(gray), 1, W, W * H, 2, N.ptr(m1), N.ptr(m2), N.ptr(out), None))
+    for f in range(2):
+        assert np.array_equal(out[f], O.remap_linear(gray[f], m1, m2))
+    N.check(emu, emu.ovo_rectify(c.ctx, N.ptr(bgr), 3, 3 * W, 3 * W * H, 2, N.ptr(m1), N.ptr(m2), N.ptr(out), None))
+    for f in range(2):
+        assert np.array_equal(out[f], O.remap_linear(O.bgr2gray(bgr[f]), m1, m2))
+    N.check(emu, emu.ovo_rectify(c.ctx, N.ptr(bgr), 3, 3 * W, 3 * W * H, 2, None, None, N.ptr(out), None))
+    for f in range(2):
+        assert np.array_equal(out[f], O.bgr2gray(bgr[f]))

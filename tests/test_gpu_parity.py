@@ -128,9 +128,9 @@ def test_compute_3d_matches_reference_contract():
 
 def _replay(g, **kw):
     W, H, D, n = int(g["W"]), int(g["H"]), int(g["D"]), int(g["nfeatures"])
-    cam, _ = _cam(W, H, D)
+    cam = StereoCamera(**(synth.camera_args_distorted if bool(g["distorted"]) else synth.camera_args)(W, H, D))
     assert tuple(cam.valid_region_left) == tuple(int(v) for v in g["roi"])
-    od = StereoOdometer(cam, nfeatures=n, preprocessed_frames=True, **kw)
+    od = StereoOdometer(cam, nfeatures=n, preprocessed_frames=bool(g["preprocessed"]), **kw)
     for i in range(len(g["left"])):
         ok = od.update(g["left"][i], g["right"][i])
         assert ok == bool(g["ok_%d" % i]), i
@@ -145,7 +145,7 @@ def _replay(g, **kw):
     return od
 
 
-@pytest.mark.parametrize("name,kw", [("seq_small", {}), ("seq_skip", {}),
+@pytest.mark.parametrize("name,kw", [("seq_small", {}), ("seq_skip", {}), ("seq_rectify", {}),
                                      ("seq_filters", dict(rigidity_threshold=0.06, outlier_threshold=0.02))])
 def test_update_reproduces_reference_fixtures(golden, name, kw):
     _replay(golden(name), **kw)
@@ -201,3 +201,23 @@ def test_batch_odometer_equals_single_stream(golden):
         assert np.array_equal(bo.odometers[s].c_T_w, singles[s].c_T_w)
         assert bo.odometers[s].skip_cause == singles[s].skip_cause
         assert bo.odometers[s].skipped_frames == singles[s].skipped_frames
+
+
+def test_rectify_and_gray_bit_exact():
+    import cv2
+    W, H = 480, 160
+    args = synth.camera_args_distorted(W, H, 64)
+    cam = StereoCamera(**args)
+    rng = np.random.default_rng(8)
+    img = rng.integers(0, 256, (H, W), dtype=np.uint8)
+    assert np.array_equal(cam.undistort_rectify_left(img), cv2.remap(img, cam.map_left_1, cam.map_left_2, cv2.INTER_LINEAR))
+    assert np.array_equal(cam.undistort_rectify_right(img), cv2.remap(img, cam.map_right_1, cam.map_right_2, cv2.INTER_LINEAR))
+    # colour + remap through compute_3d vs the cv2-backed port
+    Ls, Rs, _ = synth.make_sequence(W, H, 1)
+    Lc, Rc = synth.to_bgr(Ls[0], 1), synth.to_bgr(Rs[0], 2)
+    port = O.StereoCameraPort(**args, backend="cv2")
+    for pre in (False, True):
+        xyz, disp, left = cam.compute_3d(Lc, Rc, preprocessed=pre)
+        rxyz, rdisp, rleft = port.compute_3d(Lc, Rc, preprocessed=pre)
+        assert np.array_equal(left, rleft) and np.array_equal(disp, rdisp)
+        assert np.array_equal(xyz.view(np.uint32), rxyz.view(np.uint32))

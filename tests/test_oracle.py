@@ -81,6 +81,21 @@ def test_reproject_restated_equals_cv2():
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
 
 
+def test_remap_and_gray_restated_equal_cv2():
+    rng = np.random.default_rng(6)
+    args = synth.camera_args_distorted(320, 200, 32)
+    cam = O.StereoCameraPort(**args, backend="cv2")
+    img = rng.integers(0, 256, (200, 320), dtype=np.uint8)
+    for m1, m2 in ((cam.map_left_1, cam.map_left_2), (cam.map_right_1, cam.map_right_2)):
+        assert np.array_equal(O.remap_linear(img, m1, m2), cv2.remap(img, m1, m2, cv2.INTER_LINEAR))
+    # maps that leave the image on every side (BORDER_CONSTANT taps)
+    m1 = np.stack([rng.integers(-3, 323, (200, 320)), rng.integers(-3, 203, (200, 320))], -1).astype(np.int16)
+    m2 = rng.integers(0, 1024, (200, 320)).astype(np.uint16)
+    assert np.array_equal(O.remap_linear(img, m1, m2), cv2.remap(img, m1, m2, cv2.INTER_LINEAR))
+    bgr = rng.integers(0, 256, (200, 320, 3), dtype=np.uint8)
+    assert np.array_equal(O.bgr2gray(bgr), cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY))
+
+
 def test_umeyama_restated_equals_cv2():
     rng = np.random.default_rng(4)
     src = rng.normal(0, 5, (200, 3)).astype(np.float32)
@@ -110,10 +125,10 @@ def test_kat_hashes_match_survey_appendix_b():
 
 def _replay(g, backend, **kw):
     W, H, D, n = int(g["W"]), int(g["H"]), int(g["D"]), int(g["nfeatures"])
-    args = synth.camera_args(W, H, D)
+    args = (synth.camera_args_distorted if bool(g["distorted"]) else synth.camera_args)(W, H, D)
     cam = O.StereoCameraPort(**args, backend=backend)
     assert tuple(cam.valid_region_left) == tuple(int(v) for v in g["roi"])
-    od = O.StereoOdometerPort(cam, nfeatures=n, preprocessed_frames=True, **kw)
+    od = O.StereoOdometerPort(cam, nfeatures=n, preprocessed_frames=bool(g["preprocessed"]), **kw)
     for i in range(len(g["left"])):
         ok = od.update(g["left"][i], g["right"][i])
         assert ok == bool(g["ok_%d" % i]), i
@@ -128,7 +143,7 @@ def _replay(g, backend, **kw):
 
 
 @pytest.mark.parametrize("backend", ["cv2", "restated"])
-@pytest.mark.parametrize("name,kw", [("seq_small", {}), ("seq_skip", {}),
+@pytest.mark.parametrize("name,kw", [("seq_small", {}), ("seq_skip", {}), ("seq_rectify", {}),
                                      ("seq_filters", dict(rigidity_threshold=0.06, outlier_threshold=0.02))])
 def test_port_reproduces_reference_fixtures(golden, backend, name, kw):
     _replay(golden(name), backend, **kw)

@@ -31,11 +31,13 @@ def kp_array(kps):
     return np.array([[k.pt[0], k.pt[1], k.size, k.angle, k.response, k.octave] for k in kps], np.float32).reshape(-1, 6)
 
 
-def run_sequence(name, W, H, D, n, lefts, rights, **od_kw):
-    args = synth.camera_args(W, H, D)
+def run_sequence(name, W, H, D, n, lefts, rights, distorted=False, **od_kw):
+    args = (synth.camera_args_distorted if distorted else synth.camera_args)(W, H, D)
     cam = openVO.StereoCamera(**args)
-    od = openVO.StereoOdometer(cam, nfeatures=n, preprocessed_frames=True, **od_kw)
-    rec = dict(roi=np.array(cam.valid_region_left), Q=cam.Q, W=W, H=H, D=D, nfeatures=n)
+    od_kw.setdefault("preprocessed_frames", True)
+    od = openVO.StereoOdometer(cam, nfeatures=n, **od_kw)
+    rec = dict(roi=np.array(cam.valid_region_left), Q=cam.Q, W=W, H=H, D=D, nfeatures=n, distorted=np.array(distorted),
+               preprocessed=np.array(od_kw["preprocessed_frames"]))
     for i in range(len(lefts)):
         ok = od.update(lefts[i], rights[i])
         rec["ok_%d" % i] = np.array(ok)
@@ -71,6 +73,10 @@ def main():
     run_sequence("seq_skip", W, H, D, n, lefts, rights)
     # 3. optional filters on
     run_sequence("seq_filters", W, H, D, n, Ls, Rs, rigidity_threshold=0.06, outlier_threshold=0.02)
+    # 3b. the reference's DEFAULT path: colour input + cv2.remap rectification (preprocessed_frames=False), distorted rig
+    Lc = np.stack([synth.to_bgr(Ls[i], seed=i) for i in range(3)])
+    Rc = np.stack([synth.to_bgr(Rs[i], seed=100 + i) for i in range(3)])
+    run_sequence("seq_rectify", W, H, D, n, Lc, Rc, distorted=True, preprocessed_frames=False)
     # 4. per-seam vectors on a KAT pair incl. matcher output
     L, R = synth.kat_pair(W, H, d=12)
     sg = cv2.StereoSGBM_create(0, D, 5, 200, 800, 1, 63, 10, 100, 2).compute(L, R)
