@@ -27,6 +27,7 @@ sys.path.insert(0, ROOT)
 CONFIGS = {
     "K": dict(W=1241, H=376, D=128, n=2000, name="KITTI-shaped 1241x376 stereo, ORB 2000 kp, StereoSGBM 128 disp"),
     "F": dict(W=1920, H=1080, D=256, n=5000, name="1920x1080 stereo, ORB 5000 kp, StereoSGBM 256 disp"),
+    "U": dict(W=3840, H=2160, D=256, n=10000, name="3840x2160 stereo, ORB 10000 kp, StereoSGBM 256 disp"),
     "S": dict(W=640, H=200, D=64, n=500, name="small 640x200 stereo, ORB 500 kp, StereoSGBM 64 disp (dev only)"),
 }
 N_DISTINCT = 6  # distinct rendered frames; sequences ping-pong through them with different phases
@@ -169,8 +170,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="K", choices=list(CONFIGS))
-    ap.add_argument("--seqs", type=int, default=16, help="independent sequences (= frames per step) per GPU")
-    ap.add_argument("--threads", type=int, default=2, help="host threads (each with its own CUDA stream and share of the sequences)")
+    ap.add_argument("--seqs", type=int, default=24, help="independent sequences (= frames per step) per GPU")
+    ap.add_argument("--threads", type=int, default=3, help="host threads (each with its own CUDA stream and share of the sequences)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--_cpu_worker", nargs=5, default=None)
     a = ap.parse_args()
@@ -243,7 +244,7 @@ def main():
         for s in range(first_step, first_step + steps):
             idx = [frame_index(s, rank * S + t * SP + q) for q in range(SP)]
             if host:
-                res = bo.update(L[idx], R[idx])
+                res = bo.update([L[i] for i in idx], [R[i] for i in idx])  # one host array per sequence, as a loader would hand them over
             else:
                 ti = torch.tensor(idx, device="cuda")
                 res = bo.update_device(dev_L[ti], dev_R[ti])

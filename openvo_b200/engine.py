@@ -88,7 +88,15 @@ class Engine:
         return buf
 
     def upload(self, arr, key):
-        """numpy uint8 [H,W] or [nb,H,W] -> device tensor via a pinned staging buffer."""
+        """numpy uint8 [nb,H,W(,3)] (or a list of nb frames) -> device tensor via a pinned staging buffer (one host copy)."""
+        if isinstance(arr, (list, tuple)):
+            first = np.asarray(arr[0])
+            stage = self._pinned(key, (len(arr),) + first.shape, torch.uint8)
+            view = stage.numpy()
+            for i, fr in enumerate(arr):
+                view[i] = fr
+            self._h2d += view.nbytes
+            return stage.to(self.device, non_blocking=True)
         a = np.ascontiguousarray(arr)
         stage = self._pinned(key, a.shape, torch.uint8)
         stage.numpy()[...] = a

@@ -119,13 +119,19 @@ class StereoCamera:
         (ref: src/openVO/stereo_camera.py:44-50: cvtColor if colour, remap unless preprocessed — both on the device)."""
         out = []
         for side, img in (("left", img_left), ("right", img_right)):
-            img = np.asarray(img)
             hw = (self.img_size[1], self.img_size[0])
-            if img.shape[:2] == hw and img.ndim in (2, 3):  # a single frame
-                img = img[None]
-            self._check(img[0])
+            if isinstance(img, (list, tuple)):   # one array per sequence: copied straight into the pinned staging buffer
+                for fr in img:
+                    self._check(np.asarray(fr))
+                colour = np.asarray(img[0]).ndim == 3
+            else:
+                img = np.asarray(img)
+                if img.shape[:2] == hw and img.ndim in (2, 3):  # a single frame
+                    img = img[None]
+                self._check(img[0])
+                colour = img.ndim == 4
             dev = eng.upload(img, key + "_" + side)
-            if img.ndim == 4 or not preprocessed:
+            if colour or not preprocessed:
                 dev = eng.rectify(dev, None if preprocessed else self._maps(eng, side))
             out.append(dev)
         if out[0].shape != out[1].shape:

@@ -131,6 +131,11 @@ def check_sequence(W, H, D, n, nframes, tag):
 def main():
     print(torch.cuda.get_device_name(0), flush=True)
     quick = "--quick" in sys.argv
+    if "--only4k" in sys.argv:
+        check_sgbm(3840, 2160, 256, "U", occl=False)
+        check_orb(3840, 2160, 10000, "U")
+        check_knn(10000, 10000, "U")
+        return
     check_sgbm(200, 60, 32, "small32")
     check_sgbm(320, 48, 64, "small64", blockSize=3, P1=72, P2=288, uniquenessRatio=0, speckleWindowSize=0)
     check_sgbm(240, 64, 48, "pad48", blockSize=7, preFilterCap=15, uniquenessRatio=15, disp12MaxDiff=2, speckleWindowSize=50, speckleRange=1)
@@ -147,6 +152,10 @@ def main():
         check_sgbm(1920, 1080, 256, "F", occl=False)
         check_orb(1920, 1080, 5000, "F")
         check_knn(5000, 5000, "F")
+    if "--4k" in sys.argv:
+        check_sgbm(3840, 2160, 256, "U", occl=False)
+        check_orb(3840, 2160, 10000, "U")
+        check_knn(10000, 10000, "U")
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "gpu_check.json"), "w") as fh:
         json.dump(OUT, fh, indent=1)
