@@ -112,6 +112,15 @@ int ovo_match_points(ovo_ctx* ctx, const int32_t* nn_dev, int nq, double match_t
 int ovo_rigid_transform(ovo_ctx* ctx, const float* pts1_dev, const float* pts2_dev, const int32_t* count_dev, int cap,
                         double* out_dev, void* stream);
 
+/* §8(f) n3 — the optional pre-filters of StereoOdometer.point_cloud_transform (off by default in the reference).
+ * ovo_rigid_body_filter replaces rigid_body_filter + the boolean-mask indexing (ref: src/openVO/stereo_odometer.py:82-105,178-181):
+ * greedy clique on the graph | ||p_i-p_j|| - ||q_i-q_j|| | < thr (float32, as numpy evaluates it), points compacted in place and
+ * *count_dev updated.  ovo_outlier_filter replaces the single-pass outlier removal (ref: :189-197): relative residual under T
+ * (f64 [12], rows of [R|t], e.g. the output of ovo_rigid_transform), keep residual < thr + median.  cap <= 4095. */
+int ovo_rigid_body_filter(ovo_ctx* ctx, float* pts_prev_dev, float* pts_cur_dev, int32_t* count_dev, int cap, double thr, void* stream);
+int ovo_outlier_filter(ovo_ctx* ctx, float* pts_prev_dev, float* pts_cur_dev, int32_t* count_dev, int cap, const double* T_dev,
+                       double thr, void* stream);
+
 /* Batched form of S-E + a8/S-F + S-G for n independent frame pairs (n <= max_batch): 2-NN, ratio test + fused 3-D lookup and
  * rigid alignment of every pair in four launches.  `items` is a HOST array; all pointers inside are device pointers.
  * out: f64 [18] per pair = the 16 values of ovo_rigid_transform followed by the two int32 counts of ovo_match_points packed in

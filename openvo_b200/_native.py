@@ -54,6 +54,8 @@ _SIGNATURES = {
     "ovo_knn2_hamming": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),
     "ovo_match_points": (_i, [_vp, _vp, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ovo_rigid_transform": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "ovo_rigid_body_filter": (_i, [_vp, _vp, _vp, _vp, _i, _d, _vp]),
+    "ovo_outlier_filter": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _d, _vp]),
     "ovo_pair_batch": (_i, [_vp, _i, ctypes.POINTER(PairItem), _d, _vp]),
     "ovo_launch_count": (ctypes.c_longlong, []),
     "ovo_transfer_bytes": (None, [_vp, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong)]),

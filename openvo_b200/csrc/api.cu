@@ -60,6 +60,9 @@ int disp_post_launch(const int16_t* disp, int W, int H, int x0, int y0, int cw, 
                      uint8_t* mask, int nb, cudaStream_t st);
 int pair_batch_launch(const GatherParams& gp, int n, const void* items_host, int cap, cudaStream_t st);
 int pair_item_size();
+size_t filter_scratch_bytes(int cap);
+int rigid_filter_launch(float* prev, float* cur, int32_t* count, int cap, float thr, uint8_t* scratch, cudaStream_t st);
+int outlier_filter_launch(float* prev, float* cur, int32_t* count, int cap, const double* T, double thr, uint8_t* scratch, cudaStream_t st);
 int rectify_launch(const uint8_t* img, int pitch, size_t frame_stride, int ch, int W, int H, int nb, const int16_t* map1,
                    const uint16_t* map2, uint8_t* out, cudaStream_t st);
 int pair_max_batch();
@@ -70,7 +73,7 @@ struct Layout {
     OrbDims orb;
     int x0, y0, cw, ch;
     size_t sgbm_bytes, orb_bytes, frame_bytes;  // per frame
-    size_t tab_bytes, knn_bytes, nsel_bytes, total;
+    size_t tab_bytes, knn_bytes, nsel_bytes, filter_bytes, total;
     int tab_off[2 * ORB_NLEVELS], tab_total;
 };
 
@@ -111,7 +114,8 @@ static int make_layout(const ovo_config* c, Layout* L) {
     L->tab_bytes = align_up((size_t)L->tab_total * 4, 256);
     L->knn_bytes = align_up(knn2_scratch_bytes(L->orb.kp_cap, L->orb.kp_cap), 256) * c->max_batch;
     L->nsel_bytes = align_up((size_t)c->max_batch * 4, 256);
-    L->total = L->frame_bytes * c->max_batch + L->tab_bytes + L->knn_bytes + L->nsel_bytes + 256;
+    L->filter_bytes = align_up(filter_scratch_bytes(L->orb.kp_cap), 256);
+    L->total = L->frame_bytes * c->max_batch + L->tab_bytes + L->knn_bytes + L->nsel_bytes + L->filter_bytes + 256;
     return 0;
 }
 
@@ -128,6 +132,7 @@ struct ovo_ctx {
     int32_t* tab_dev;
     uint32_t* knn_scratch;
     int32_t* nsel_dev;
+    uint8_t* filter_scratch;
     // pinned host staging for the keypoint selection
     int32_t* h_lvl;    // [max_batch][32]
     float* h_resp;     // [max_batch][cand_cap][2]
@@ -225,7 +230,8 @@ ovo_ctx* ovo_create(const ovo_config* cfg, void* workspace_dev, size_t workspace
     uint8_t* p = c->base + L.frame_bytes * cfg->max_batch;
     c->tab_dev = (int32_t*)p; p += L.tab_bytes;
     c->knn_scratch = (uint32_t*)p; p += L.knn_bytes;
-    c->nsel_dev = (int32_t*)p;
+    c->nsel_dev = (int32_t*)p; p += L.nsel_bytes;
+    c->filter_scratch = p;
     std::vector<int32_t> tab(L.tab_total);
     int tot;
     orb_make_resize_tables(L.orb, tab.data(), c->L.tab_off, &tot);
@@ -366,6 +372,18 @@ int ovo_pair_batch(ovo_ctx* c, int n, const ovo_pair_item* items, double thr, vo
         if (pair_batch_launch(p, m, tmp.data(), c->L.orb.kp_cap, (cudaStream_t)stream)) return 1;
     }
     return 0;
+}
+
+int ovo_rigid_body_filter(ovo_ctx* c, float* pts_prev, float* pts_cur, int32_t* count, int cap, double thr, void* stream) {
+    CHECK_CTX(c, 1);
+    if (cap > c->L.orb.kp_cap) { set_error("point capacity exceeds keypoint capacity"); return 1; }
+    return rigid_filter_launch(pts_prev, pts_cur, count, cap, (float)thr, c->filter_scratch, (cudaStream_t)stream);
+}
+
+int ovo_outlier_filter(ovo_ctx* c, float* pts_prev, float* pts_cur, int32_t* count, int cap, const double* T, double thr, void* stream) {
+    CHECK_CTX(c, 1);
+    if (cap > c->L.orb.kp_cap) { set_error("point capacity exceeds keypoint capacity"); return 1; }
+    return outlier_filter_launch(pts_prev, pts_cur, count, cap, T, thr, c->filter_scratch, (cudaStream_t)stream);
 }
 
 int ovo_rigid_transform(ovo_ctx* c, const float* pts1, const float* pts2, const int32_t* count, int cap, double* out, void* stream) {

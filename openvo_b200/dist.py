@@ -73,10 +73,60 @@ def gather_poses(local_T, local_status, mine, n_seq):
 
 
 def replay_chains(T, status):
-    """Serial product c_T_w <- T_t @ c_T_w over the committed frames of every sequence (ref: stereo_odometer.py:136-138)."""
+    """Serial replay of the pose chain of every sequence (ref: stereo_odometer.py:136-150).  status: 0 = frame not committed,
+    1 = T aligns the frame to the last committed one (c_T_w <- T @ c_T_w), 2 = fall-back alignment to the frame before it
+    (c_T_w <- T @ c_T_w_prev, the reference's second attempt)."""
     out = np.tile(np.eye(4), (T.shape[0], 1, 1))
     for s in range(T.shape[0]):
+        cur, prev = np.eye(4), np.eye(4)
         for t in range(T.shape[1]):
-            if status[s, t]:
-                out[s] = T[s, t] @ out[s]
+            if status[s, t] == 1:
+                prev, cur = cur, T[s, t] @ cur
+            elif status[s, t] == 2:
+                prev, cur = cur, T[s, t] @ prev
+        out[s] = cur
     return out
+
+
+def run_frame_chunk(odometer, lefts, rights, rank, world):
+    """BASELINE config 4: one sequence sharded by contiguous frame chunk.  This rank runs `odometer` (a fresh StereoOdometer)
+    over its chunk preceded by a one-frame halo and returns (first owned frame, T [n,4,4], status [n]) for the frames it owns.
+    Exact w.r.t. the sequential reference whenever no frame inside the first two frames of a chunk is skipped (the skip state
+    machine B4 looks two committed frames back); `status` lets the caller detect that case and re-run those frames."""
+    n_frames = len(lefts)
+    first, start, end = shard_frames(n_frames, rank, world)
+    T = np.tile(np.eye(4), (end - start, 1, 1))
+    status = np.zeros(end - start, np.int32)
+    for f in range(first, end):
+        ok = odometer.update(lefts[f], rights[f])
+        if f >= start and f > 0:
+            status[f - start] = odometer.last_mode if ok else 0
+            if ok and odometer.last_T is not None and odometer.last_mode:
+                T[f - start] = odometer.last_T
+    return start, T, status
+
+
+def gather_frame_chunks(start, T, status, n_frames):
+    """All-gather the per-chunk results of run_frame_chunk -> (T [n_frames,4,4], status [n_frames]) on every rank."""
+    world = dist.get_world_size()
+    dev = _device()
+    per = (n_frames + world - 1) // world
+    pack = torch.zeros(per * 18, dtype=torch.float64, device=dev)
+    buf = np.zeros((per, 18))
+    buf[:, 0] = -1
+    k = len(status)
+    buf[:k, 0] = np.arange(start, start + k)
+    buf[:k, 1] = status
+    buf[:k, 2:] = T.reshape(k, 16)
+    pack.copy_(torch.from_numpy(buf.reshape(-1)))
+    packs = [torch.zeros_like(pack) for _ in range(world)]
+    dist.all_gather(packs, pack)
+    Tall = np.tile(np.eye(4), (n_frames, 1, 1))
+    sall = np.zeros(n_frames, np.int32)
+    for p in packs:
+        for row in p.cpu().numpy().reshape(per, 18):
+            if row[0] >= 0:
+                f = int(row[0])
+                sall[f] = int(row[1])
+                Tall[f] = row[2:].reshape(4, 4)
+    return Tall, sall

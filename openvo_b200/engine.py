@@ -206,6 +206,35 @@ class Engine:
         self.pair_async(a, b, match_threshold, 0)
         return self.pair_collect(1)[0]
 
+    def filtered_transform(self, pts1, pts2, count_dev, rigidity_threshold, outlier_threshold, min_matches):
+        """point_cloud_transform with the optional filters on (ref: stereo_odometer.py:177-205), on device buffers
+        pts1/pts2 [cap,3] and a device count (all modified in place).  Returns (n_after_rigidity, n_final, out16 or None)."""
+        st = self._stream()
+        cap = pts1.shape[0]
+        host = torch.empty(1, dtype=torch.int32).pin_memory()
+
+        def read_count():
+            host.copy_(count_dev, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            self._d2h += 4
+            return int(host[0])
+        out = torch.empty(16, dtype=torch.float64, device=self.device)
+        if rigidity_threshold > 0:
+            N.check(self.lib, self.lib.ovo_rigid_body_filter(self.ctx, pts1.data_ptr(), pts2.data_ptr(), count_dev.data_ptr(), cap,
+                                                             float(np.float32(rigidity_threshold)), st))
+        n1 = read_count()
+        n2 = n1
+        if outlier_threshold > 0 and n1 >= 10:
+            N.check(self.lib, self.lib.ovo_rigid_transform(self.ctx, pts1.data_ptr(), pts2.data_ptr(), count_dev.data_ptr(), cap, out.data_ptr(), st))
+            N.check(self.lib, self.lib.ovo_outlier_filter(self.ctx, pts1.data_ptr(), pts2.data_ptr(), count_dev.data_ptr(), cap, out.data_ptr(),
+                                                          float(outlier_threshold), st))
+            n2 = read_count()
+        if n2 < min_matches:
+            return n1, n2, None
+        N.check(self.lib, self.lib.ovo_rigid_transform(self.ctx, pts1.data_ptr(), pts2.data_ptr(), count_dev.data_ptr(), cap, out.data_ptr(), st))
+        self._d2h += 128
+        return n1, n2, out.cpu().numpy()
+
     def rigid(self, pts1, pts2):
         """numpy float32 [m,3] x2 -> out16 (estimateAffine3D seam for the optional filter paths)."""
         m = len(pts1)

@@ -95,6 +95,7 @@ class StereoOdometer:
         self.skip_cause = ""
         self.last_match_count = 0
         self.last_T = None
+        self.last_mode = 0  # 0: frame not committed / first frame, 1: aligned to the current frame, 2: fall-back to the previous one
 
     def _engine(self):
         return self.stereo.engine(self._nfeatures, self._max_batch, float(self.MIN_VALID_DISPARITY), float(self.MAX_VALID_DISPARITY), tag=self._engine_tag)
@@ -172,6 +173,7 @@ class StereoOdometer:
     def _advance(self, frame, first=None):
         """The state machine of ``update`` for an already extracted frame.  ``first`` optionally carries the device result
         of the (current -> frame) pair step when a batch driver has already launched it."""
+        self.last_mode = 0
         if frame.n_kp < self.min_matches:
             self.skipped_frames += 1
             self.skip_cause = "keypoints"
@@ -183,6 +185,7 @@ class StereoOdometer:
         if T is not None:
             self.c_T_w_prev = self.c_T_w
             self.c_T_w = T @ self.c_T_w
+            self.last_mode = 1
         if T is None and self._prev is not None:
             T = self._relative(self._prev, frame)
             if T is not None:
@@ -190,6 +193,7 @@ class StereoOdometer:
                 self.c_T_w_prev = self.c_T_w
                 self.c_T_w = T @ older
                 self.skipped_frames = 0
+                self.last_mode = 2
         if T is None:
             self.skipped_frames += 1
             return False
@@ -215,7 +219,9 @@ class StereoOdometer:
         if bad:
             raise ZeroDivisionError("division by zero")  # ref: stereo_odometer.py:79 with every tap skipped
         if self.rigidity_threshold > 0 or self.outlier_threshold > 0:
-            return self.point_cloud_transform(eng.pts1[slot, :n].cpu().numpy(), eng.pts2[slot, :n].cpu().numpy())
+            import torch
+            cnt = torch.tensor([n], dtype=torch.int32, device=eng.device)
+            return self._filtered(eng.pts1[slot], eng.pts2[slot], cnt)
         if n < 10:
             self.skip_cause = "rigidity"
         return self._gate(out)
@@ -247,7 +253,7 @@ class StereoOdometer:
         return np.array(pts1), np.array(pts2)
 
     def rigid_body_filter(self, prev_pts, pts):
-        """ref: src/openVO/stereo_odometer.py:82-105 (off by default; SURVEY.md §8(f) n3 — host numpy for now)."""
+        """ref: src/openVO/stereo_odometer.py:82-105 for callers that hold host arrays; ``update`` runs ovo_rigid_body_filter."""
         d_now = np.linalg.norm(pts[:, None, :] - pts[None, :, :], axis=2)
         d_old = np.linalg.norm(prev_pts[:, None, :] - prev_pts[None, :, :], axis=2)
         consistency = (np.abs(d_now - d_old) < self.rigidity_threshold).astype(int)
@@ -264,32 +270,33 @@ class StereoOdometer:
             compatible = (consistency @ clique >= clique.sum()).astype(int)
         return clique
 
-    def _rigid(self, a, b):
-        out = self._engine().rigid(a, b)
-        return out
-
-    def point_cloud_transform(self, current_pts, next_pts):
-        """ref: src/openVO/stereo_odometer.py:177-223."""
-        if self.rigidity_threshold > 0:
-            inl = self.rigid_body_filter(current_pts, next_pts)
-            current_pts, next_pts = current_pts[inl > 0], next_pts[inl > 0]
-        rigidity_cause = False
-        if len(current_pts) < 10:
-            rigidity_cause = True
+    def _filtered(self, pts1_dev, pts2_dev, count_dev):
+        """ref: src/openVO/stereo_odometer.py:177-223 with the optional filters, on device buffers."""
+        n1, n2, out = self._engine().filtered_transform(pts1_dev, pts2_dev, count_dev, self.rigidity_threshold, self.outlier_threshold,
+                                                        self.min_matches)
+        rigidity_cause = n1 < 10
+        if rigidity_cause:
             self.skip_cause = "rigidity"
-        if self.outlier_threshold > 0 and len(current_pts) >= 10:
-            T = np.eye(4)
-            T[:3, :4] = self._rigid(current_pts, next_pts)[:12].reshape(3, 4)
-            hn = np.hstack([next_pts, np.ones((len(next_pts), 1))])
-            hp = np.hstack([current_pts, np.ones((len(current_pts), 1))])
-            err = np.linalg.norm(hn - hp @ T.T, axis=1) / np.linalg.norm(hn, axis=1)
-            thr = self.outlier_threshold + np.median(err)
-            current_pts, next_pts = current_pts[err < thr], next_pts[err < thr]
-        if len(current_pts) < self.min_matches:
+        if out is None:
             if not rigidity_cause:
                 self.skip_cause = "outlier"
             return None
-        return self._gate(self._rigid(current_pts, next_pts))
+        return self._gate(out)
+
+    def point_cloud_transform(self, current_pts, next_pts):
+        """ref: src/openVO/stereo_odometer.py:177-223 for callers that hold host-side point sets (numpy float32 [m,3])."""
+        import torch
+        eng = self._engine()
+        m = len(current_pts)
+        if m > eng.kp_cap:
+            raise ValueError("more points than the keypoint capacity")
+        p1 = torch.zeros((eng.kp_cap, 3), dtype=torch.float32, device=eng.device)
+        p2 = torch.zeros((eng.kp_cap, 3), dtype=torch.float32, device=eng.device)
+        if m:
+            p1[:m] = torch.from_numpy(np.ascontiguousarray(current_pts, np.float32)).to(eng.device)
+            p2[:m] = torch.from_numpy(np.ascontiguousarray(next_pts, np.float32)).to(eng.device)
+        cnt = torch.tensor([m], dtype=torch.int32, device=eng.device)
+        return self._filtered(p1, p2, cnt)
 
     def current_pose(self):
         # ref: src/openVO/stereo_odometer.py:225-226

@@ -29,15 +29,25 @@ def _worker(rank, world, port, q):
         local_s = status[mine]
         T, s, owner = D.gather_poses(local_T, local_s, mine, n_seq)
         assert np.array_equal(T, allT) and np.array_equal(s, status)
-        chains = D.replay_chains(T, s)
+        status[2, 4] = 2  # a fall-back alignment replaces the previous frame's transform
+        chains = D.replay_chains(T, status)
         ref = []
         for i in range(n_seq):
-            c = np.eye(4)
+            c, p = np.eye(4), np.eye(4)
             for j in range(n_frames):
-                if status[i, j]:
-                    c = allT[i, j] @ c
+                if status[i, j] == 1:
+                    p, c = c, allT[i, j] @ c
+                elif status[i, j] == 2:
+                    p, c = c, allT[i, j] @ p
             ref.append(c)
         assert np.abs(chains - np.stack(ref)).max() < 1e-12
+        # frame-chunk gather: every rank contributes its contiguous chunk of one sequence
+        nfr = 7
+        first, start, end = D.shard_frames(nfr, rank, world)
+        Tc = allT[0, :1].repeat(end - start, 0) * (np.arange(start, end)[:, None, None] + 1)
+        sc = np.ones(end - start, np.int32)
+        Tg, sg = D.gather_frame_chunks(start, Tc, sc, nfr)
+        assert sg.tolist() == [1] * nfr and np.allclose(Tg[5], allT[0, 0] * 6)
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         q.put((rank, repr(e)))

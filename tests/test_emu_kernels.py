@@ -186,3 +186,44 @@ def test_rectify_kernel(emu):
     N.check(emu, emu.ovo_rectify(c.ctx, N.ptr(bgr), 3, 3 * W, 3 * W * H, 2, None, None, N.ptr(out), None))
     for f in range(2):
         assert np.array_equal(out[f], O.bgr2gray(bgr[f]))
+
+
+def test_pose_filter_kernels(emu):
+    """ovo_rigid_body_filter / ovo_outlier_filter vs the reference's numpy formulation (oracle port)."""
+    rng = np.random.default_rng(11)
+    W, H, n = 300, 150, 300
+    c = Ctx(emu, W, H, sgbm_params(32), (0, 0, W, H), np.eye(4), n)
+    m = 180
+    ang = 0.03
+    Rm = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]])
+    prev = rng.uniform(-5, 5, (m, 3)).astype(np.float32) + np.float32([0, 0, 12])
+    cur = (prev @ Rm.T + [0.05, 0.0, 0.2] + rng.normal(0, 0.01, (m, 3))).astype(np.float32)
+    bad = rng.choice(m, 40, replace=False)
+    cur[bad] += rng.normal(0, 1.0, (40, 3)).astype(np.float32)
+
+    class Dummy:
+        backend_name, sgbm_params = "restated", sgbm_params(32)
+    port = O.StereoOdometerPort(Dummy(), nfeatures=0, rigidity_threshold=0.06, outlier_threshold=0.02)
+    clique = port.rigid_body_filter(prev, cur)
+    a, b = np.zeros((c.cap, 3), np.float32), np.zeros((c.cap, 3), np.float32)
+    a[:m], b[:m] = prev, cur
+    cnt = np.array([m], np.int32)
+    N.check(emu, emu.ovo_rigid_body_filter(c.ctx, N.ptr(a), N.ptr(b), N.ptr(cnt), c.cap, float(np.float32(0.06)), None))
+    k = int(clique.sum())
+    assert cnt[0] == k and 100 < k < m
+    assert np.array_equal(a[:k], prev[clique > 0]) and np.array_equal(b[:k], cur[clique > 0])
+    # outlier filter on the survivors
+    p, q = prev[clique > 0], cur[clique > 0]
+    q = q.copy()
+    q[::9] += np.float32(0.8)
+    b[:k] = q
+    T, _ = O.umeyama(p, q)
+    T4 = np.vstack([T, [0, 0, 0, 1]])
+    hn = np.hstack([q, np.ones((k, 1))])
+    hp = np.hstack([p, np.ones((k, 1))])
+    err = np.array([np.linalg.norm(hn[i] - T4 @ hp[i]) / np.linalg.norm(hn[i]) for i in range(k)])
+    keep = err < 0.02 + np.median(err)
+    Tdev = np.ascontiguousarray(T.reshape(-1))
+    N.check(emu, emu.ovo_outlier_filter(c.ctx, N.ptr(a), N.ptr(b), N.ptr(cnt), c.cap, N.ptr(Tdev), 0.02, None))
+    assert cnt[0] == keep.sum() and 0 < keep.sum() < k
+    assert np.array_equal(a[:cnt[0]], p[keep]) and np.array_equal(b[:cnt[0]], q[keep])

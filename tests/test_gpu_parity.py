@@ -221,3 +221,22 @@ def test_rectify_and_gray_bit_exact():
         rxyz, rdisp, rleft = port.compute_3d(Lc, Rc, preprocessed=pre)
         assert np.array_equal(left, rleft) and np.array_equal(disp, rdisp)
         assert np.array_equal(xyz.view(np.uint32), rxyz.view(np.uint32))
+
+
+def test_frame_chunk_sharding_equals_sequential(golden):
+    # config 4 plumbing: two "ranks" run their frame chunks (with a one-frame halo) independently; the replayed chain equals
+    # the sequential odometer's
+    from openvo_b200 import dist as D
+    g = golden("seq_small")
+    W, H, Dn, n = int(g["W"]), int(g["H"]), int(g["D"]), int(g["nfeatures"])
+    cam, _ = _cam(W, H, Dn)
+    nfr = len(g["left"])
+    Tall = np.tile(np.eye(4), (nfr, 1, 1))
+    sall = np.zeros(nfr, np.int32)
+    for rank in range(2):
+        od = StereoOdometer(cam, nfeatures=n, preprocessed_frames=True)
+        start, T, st = D.run_frame_chunk(od, g["left"], g["right"], rank, 2)
+        Tall[start:start + len(st)] = T
+        sall[start:start + len(st)] = st
+    chain = D.replay_chains(Tall[None], sall[None])[0]
+    assert _pose_close(chain, g["cTw_%d" % (nfr - 1)])
