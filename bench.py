@@ -182,7 +182,7 @@ def main():
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
-    workload = "synthetic %s, %d independent sequences per GPU, 1 frame each per step" % (cfg["name"], a.seqs)
+    workload = "synthetic %s, independent sequences advanced 1 frame each per step" % cfg["name"]
     metric, unit = "stereo frames/sec", "frames/s"
 
     L, R = make_frames(cfg)
@@ -195,8 +195,8 @@ def main():
         sample = "%d processes x %d frames each (cv2.setNumThreads(1)), wall %.1f s" % (cores, a.steps, wall)
         line = {"impl": "reference", "metric": metric, "value": fps, "unit": unit, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": 1e3 * wall / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i16",
-                "data": "synthetic", "config": {"workload": "synthetic %s, one sequence per host core, 1 frame each per step" % cfg["name"],
-                                                "frames_per_step": cores},
+                "data": "synthetic", "config": {"workload": workload, "frames_per_step": cores, "sequences": cores,
+                                                "note": "one sequence per host core"},
                 "cpu_baseline": {"value": fps, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
                 "e2e": {"value": fps, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         print(json.dumps(line))

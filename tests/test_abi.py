@@ -60,10 +60,13 @@ def test_no_gpu_fails_loudly():
 
 
 def test_product_never_imports_oracle():
+    """oracle/ is test infrastructure: nothing under openvo_b200/ may import, link or execute it."""
+    import re
     pkg = os.path.join(ROOT, "openvo_b200")
+    pat = re.compile(r"^\s*(from\s+oracle|import\s+oracle|#include\s+\".*oracle)", re.M)
     for dp, _, files in os.walk(pkg):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(dp, f)).read()
-                assert "oracle" not in src.replace("oracle =", "").replace("oracle/", "").lower() or f in ("orb.cu", "sgbm.cu", "match.cu"), f
-                assert "import oracle" not in src and "from oracle" not in src, f
+                assert not pat.search(src), f
+                assert "oracle/_build" not in src and "liboracle" not in src, f
