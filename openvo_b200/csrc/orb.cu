@@ -80,14 +80,29 @@ __device__ __forceinline__ int arc9_max_of_min(const int (&v)[16]) {
 
 constexpr int kFastTX = 32, kFastTY = 8;
 
+__device__ __forceinline__ void fast_ring(const uint8_t (*tile)[kFastTX + 8], int cx, int cy, int (&v)[16]) {
+    const int c = tile[cy][cx];
+    v[0] = c - tile[cy + 3][cx];      v[1] = c - tile[cy + 3][cx + 1];  v[2] = c - tile[cy + 2][cx + 2];  v[3] = c - tile[cy + 1][cx + 3];
+    v[4] = c - tile[cy][cx + 3];      v[5] = c - tile[cy - 1][cx + 3];  v[6] = c - tile[cy - 2][cx + 2];  v[7] = c - tile[cy - 3][cx + 1];
+    v[8] = c - tile[cy - 3][cx];      v[9] = c - tile[cy - 3][cx - 1];  v[10] = c - tile[cy - 2][cx - 2]; v[11] = c - tile[cy - 1][cx - 3];
+    v[12] = c - tile[cy][cx - 3];     v[13] = c - tile[cy + 1][cx - 3]; v[14] = c - tile[cy + 2][cx - 2]; v[15] = c - tile[cy + 3][cx - 1];
+}
+
+// Two passes per tile so that the expensive score (max over arcs of min over 9) runs densely on corner pixels only: pass A is
+// the 9-contiguous test on brighter / darker bit masks for every pixel (non-corners store 0), corners are queued in shared
+// memory; pass B scores the queue.
 __global__ void __launch_bounds__(kFastTX* kFastTY) k_orb_fast(OrbDims d, OrbWorkspace ws, size_t ws_stride) {
     __shared__ uint8_t tile[kFastTY + 6][kFastTX + 8];
+    __shared__ uint16_t queue[kFastTX * kFastTY];
+    __shared__ int nq;
     const int level = blockIdx.z % ORB_NLEVELS, f = blockIdx.z / ORB_NLEVELS;
     const OrbLevel L = d.lv[level];
     const int x0 = blockIdx.x * kFastTX, y0 = blockIdx.y * kFastTY;
     if (x0 >= L.w || y0 >= L.h) return;
     const uint8_t* img = fptr(ws.pyr, ws_stride, f) + L.off;
+    uint8_t* out = fptr(ws.score, ws_stride, f) + L.off;
     const int tid = threadIdx.y * kFastTX + threadIdx.x;
+    if (tid == 0) nq = 0;
     for (int i = tid; i < (kFastTY + 6) * (kFastTX + 6); i += kFastTX * kFastTY) {
         const int ty = i / (kFastTX + 6), tx = i % (kFastTX + 6);
         const int gx = min(max(x0 + tx - 3, 0), L.w - 1), gy = min(max(y0 + ty - 3, 0), L.h - 1);
@@ -95,49 +110,41 @@ __global__ void __launch_bounds__(kFastTX* kFastTY) k_orb_fast(OrbDims d, OrbWor
     }
     __syncthreads();
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-    if (x >= L.w || y >= L.h) return;
-    int score = 0;
-    if (x >= 3 && x < L.w - 3 && y >= 3 && y < L.h - 3) {
-        const int cx = threadIdx.x + 3, cy = threadIdx.y + 3;
-        const int c = tile[cy][cx];
-        // any 9-arc of the ring covers at least two of the four compass pixels
-        {
-            const int a0 = c - tile[cy + 3][cx], a4 = c - tile[cy][cx + 3], a8 = c - tile[cy - 3][cx], a12 = c - tile[cy][cx - 3];
-            const int nb = (a0 > kFastT) + (a4 > kFastT) + (a8 > kFastT) + (a12 > kFastT);
-            const int nd = (a0 < -kFastT) + (a4 < -kFastT) + (a8 < -kFastT) + (a12 < -kFastT);
-            if (nb < 2 && nd < 2) {
-                fptr(ws.score, ws_stride, f)[L.off + (size_t)y * L.w + x] = 0;
-                return;
+    if (x < L.w && y < L.h) {
+        bool corner = false;
+        if (x >= 3 && x < L.w - 3 && y >= 3 && y < L.h - 3) {
+            int v[16];
+            fast_ring(tile, threadIdx.x + 3, threadIdx.y + 3, v);
+            uint32_t mb = 0, md = 0;
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                mb |= (v[k] > kFastT ? 1u : 0u) << k;
+                md |= (v[k] < -kFastT ? 1u : 0u) << k;
             }
+            auto has9 = [](uint32_t m) {
+                m |= m << 16;
+                uint32_t t = m & (m >> 1);
+                t &= t >> 2;
+                t &= t >> 4;
+                t &= m >> 8;
+                return (t & 0xFFFFu) != 0;
+            };
+            corner = has9(mb) || has9(md);
         }
-        int v[16];
-        v[0] = c - tile[cy + 3][cx];      v[1] = c - tile[cy + 3][cx + 1];  v[2] = c - tile[cy + 2][cx + 2];  v[3] = c - tile[cy + 1][cx + 3];
-        v[4] = c - tile[cy][cx + 3];      v[5] = c - tile[cy - 1][cx + 3];  v[6] = c - tile[cy - 2][cx + 2];  v[7] = c - tile[cy - 3][cx + 1];
-        v[8] = c - tile[cy - 3][cx];      v[9] = c - tile[cy - 3][cx - 1];  v[10] = c - tile[cy - 2][cx - 2]; v[11] = c - tile[cy - 1][cx - 3];
-        v[12] = c - tile[cy][cx - 3];     v[13] = c - tile[cy + 1][cx - 3]; v[14] = c - tile[cy + 2][cx - 2]; v[15] = c - tile[cy + 3][cx - 1];
-        uint32_t mb = 0, md = 0;
-#pragma unroll
-        for (int k = 0; k < 16; k++) {
-            mb |= (v[k] > kFastT ? 1u : 0u) << k;
-            md |= (v[k] < -kFastT ? 1u : 0u) << k;
-        }
-        auto has9 = [](uint32_t m) {
-            m |= m << 16;
-            uint32_t t = m & (m >> 1);
-            t &= t >> 2;
-            t &= t >> 4;
-            t &= m >> 8;
-            return (t & 0xFFFFu) != 0;
-        };
-        if (has9(mb) || has9(md)) {
-            int nv[16];
-#pragma unroll
-            for (int k = 0; k < 16; k++) nv[k] = -v[k];
-            const int m = max(arc9_max_of_min(v), arc9_max_of_min(nv));
-            score = m - 1;  // largest threshold for which the pixel is still a corner
-        }
+        if (corner) queue[atomicAdd(&nq, 1)] = (uint16_t)tid;
+        else out[(size_t)y * L.w + x] = 0;
     }
-    fptr(ws.score, ws_stride, f)[L.off + (size_t)y * L.w + x] = (uint8_t)score;
+    __syncthreads();
+    const int n = nq;
+    for (int i = tid; i < n; i += kFastTX * kFastTY) {
+        const int t = queue[i], tx = t % kFastTX, ty = t / kFastTX;
+        int v[16], nv[16];
+        fast_ring(tile, tx + 3, ty + 3, v);
+#pragma unroll
+        for (int k = 0; k < 16; k++) nv[k] = -v[k];
+        const int m = max(arc9_max_of_min(v), arc9_max_of_min(nv));
+        out[(size_t)(y0 + ty) * L.w + x0 + tx] = (uint8_t)(m - 1);  // largest threshold for which the pixel is still a corner
+    }
 }
 
 // ---- NMS + mask + border, emitted in raster order --------------------------------------------------------------------------

@@ -21,7 +21,7 @@ def build(force=False):
             src = os.path.join(CSRC, f)
             if force or not os.path.exists(obj) or any(os.path.getmtime(d) > os.path.getmtime(obj) for d in deps):
                 subprocess.check_call(["g++", "-std=c++17", "-O2", "-g", "-DOVO_EMU", "-I", HERE, "-fPIC", "-mfma",
-                                       "-ffp-contract=off", "-Wno-unused-function", "-x", "c++", "-c", src, "-o", obj])
+                                       "-ffp-contract=off", "-Wno-unused-function"] + os.environ.get("OVO_EMU_DEFS", "").split() + [ "-x", "c++", "-c", src, "-o", obj])
             objs.append(obj)
         subprocess.check_call(["g++", "-shared", "-o", OUT] + objs + ["-lpthread"])
     return OUT
