@@ -45,6 +45,9 @@ typedef struct ovo_config {
     int nfeatures;           /* cv2.ORB_create(nfeatures=...) (ref: src/openVO/stereo_odometer.py:22) */
     int max_batch;           /* frames a single call may process */
     float min_valid_disparity, max_valid_disparity; /* StereoOdometer.MIN/MAX_VALID_DISPARITY (ref: stereo_odometer.py:6-7) */
+    int sgbm_mode;           /* 0 = cv2.StereoSGBM MODE_SGBM, 5 directions — what the reference uses (its `mode=1` is commented out,
+                                ref: src/openVO/stereo_camera.py:27); 1 = MODE_HH, 8 directions: opt-in extension,
+                                changes ~10 % of the output pixels, so it is never the default */
 } ovo_config;
 
 const char* ovo_last_error(void);
@@ -101,10 +104,13 @@ int ovo_knn2_hamming(ovo_ctx* ctx, const uint8_t* q_desc_dev, int nq, const uint
  * StereoOdometer.point_clouds (ref: src/openVO/stereo_odometer.py:164,170-175,50-79), with the 3-D image evaluated
  * lazily from the cropped disparity (reprojectImageTo3D fused in).
  * matches: i32 [nq][3] = (queryIdx, trainIdx, distance) in query order; pts1/pts2: f32 [nq][3];
- * counts: i32 [2] = (number of matches, number of lookups whose four taps were all unusable). */
+ * counts: i32 [2] = (number of matches, number of lookups whose four taps were all unusable).
+ * nn_rev_dev: NULL for the reference's behaviour; otherwise the 2-NN table of the TRAIN set against the QUERY set (ovo_knn2_hamming
+ * with the arguments swapped) and a match (q, t) is kept only if t's nearest neighbour is q — the left-right cross-check the reference
+ * leaves as "TODO crosscheck" (ref: src/openVO/stereo_odometer.py:21), an opt-in extension. */
 int ovo_match_points(ovo_ctx* ctx, const int32_t* nn_dev, int nq, double match_threshold, const float* kp1_dev,
                      const float* kp2_dev, const float* disp1_f32_dev, const float* disp2_f32_dev, int32_t* matches_dev,
-                     float* pts1_dev, float* pts2_dev, int32_t* counts_dev, void* stream);
+                     float* pts1_dev, float* pts2_dev, int32_t* counts_dev, const int32_t* nn_rev_dev, void* stream);
 
 /* Seam S-G — replaces cv2.estimateAffine3D(src, dst, force_rotation=True) and the quantities the gates need
  * (ref: src/openVO/stereo_odometer.py:204-221).  count_dev: i32 device scalar (number of points, e.g. counts[0]).
@@ -133,6 +139,7 @@ typedef struct ovo_pair_item {
     float *pts1, *pts2;
     double* out;
     uint32_t* scratch;
+    int32_t* nn_rev; /* NULL, or a [nt][4] buffer: enables the cross-check for this pair */
 } ovo_pair_item;
 int ovo_pair_batch(ovo_ctx* ctx, int n, const ovo_pair_item* items_host, double match_threshold, void* stream);
 

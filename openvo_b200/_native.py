@@ -22,14 +22,14 @@ class SgbmParams(ctypes.Structure):
 class Config(ctypes.Structure):
     _fields_ = [("width", ctypes.c_int), ("height", ctypes.c_int), ("sgbm", SgbmParams), ("roi", ctypes.c_int * 4),
                 ("Q", ctypes.c_double * 16), ("nfeatures", ctypes.c_int), ("max_batch", ctypes.c_int),
-                ("min_valid_disparity", ctypes.c_float), ("max_valid_disparity", ctypes.c_float)]
+                ("min_valid_disparity", ctypes.c_float), ("max_valid_disparity", ctypes.c_float), ("sgbm_mode", ctypes.c_int)]
 
 
 class PairItem(ctypes.Structure):
     _fields_ = [("q_desc", ctypes.c_void_p), ("t_desc", ctypes.c_void_p), ("nq", ctypes.c_int), ("nt", ctypes.c_int),
                 ("kp1", ctypes.c_void_p), ("kp2", ctypes.c_void_p), ("disp1", ctypes.c_void_p), ("disp2", ctypes.c_void_p),
                 ("nn", ctypes.c_void_p), ("matches", ctypes.c_void_p), ("pts1", ctypes.c_void_p), ("pts2", ctypes.c_void_p),
-                ("out", ctypes.c_void_p), ("scratch", ctypes.c_void_p)]
+                ("out", ctypes.c_void_p), ("scratch", ctypes.c_void_p), ("nn_rev", ctypes.c_void_p)]
 
 
 class NativeError(RuntimeError):
@@ -52,7 +52,7 @@ _SIGNATURES = {
     "ovo_rectify": (_i, [_vp, _vp, _i, _i, _sz, _i, _vp, _vp, _vp, _vp]),
     "ovo_orb_detect_compute": (_i, [_vp, _vp, _vp, _i, _vp, _vp, ctypes.POINTER(_i), _vp]),
     "ovo_knn2_hamming": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),
-    "ovo_match_points": (_i, [_vp, _vp, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ovo_match_points": (_i, [_vp, _vp, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ovo_rigid_transform": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "ovo_rigid_body_filter": (_i, [_vp, _vp, _vp, _vp, _i, _d, _vp]),
     "ovo_outlier_filter": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _d, _vp]),
@@ -91,7 +91,7 @@ def check(lib, rc):
         raise NativeError(lib.ovo_last_error().decode("utf-8", "replace"))
 
 
-def make_config(width, height, sgbm_params, roi, Q, nfeatures, max_batch=1, min_valid=4.0, max_valid=100.0):
+def make_config(width, height, sgbm_params, roi, Q, nfeatures, max_batch=1, min_valid=4.0, max_valid=100.0, sgbm_mode=None):
     cfg = Config()
     cfg.width, cfg.height = int(width), int(height)
     for k in SGBM_KEYS:
@@ -103,6 +103,7 @@ def make_config(width, height, sgbm_params, roi, Q, nfeatures, max_batch=1, min_
         cfg.Q[i] = flat[i]
     cfg.nfeatures, cfg.max_batch = int(nfeatures), int(max_batch)
     cfg.min_valid_disparity, cfg.max_valid_disparity = float(min_valid), float(max_valid)
+    cfg.sgbm_mode = int(sgbm_params.get("mode", 0) if sgbm_mode is None else sgbm_mode)
     return cfg
 
 

@@ -31,7 +31,7 @@ class BatchOdometer:
             if od._cur is not None and fr.n_kp >= od.min_matches and fr.n_kp >= 2:
                 jobs.append((od._cur, fr, i))
                 queued.append(i)
-        eng.pair_batch_async(jobs, self.odometers[0].match_threshold)
+        eng.pair_batch_async(jobs, self.odometers[0].match_threshold, self.odometers[0].cross_check)
         res = eng.pair_collect(self.n) if queued else []
         out = []
         for i, (od, fr) in enumerate(zip(self.odometers, frames)):

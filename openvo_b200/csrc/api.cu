@@ -94,6 +94,8 @@ static int make_layout(const ovo_config* c, Layout* L) {
     s.disp12 = p.disp12MaxDiff > 0 ? p.disp12MaxDiff : 1;
     s.ftzero = (p.preFilterCap > 15 ? p.preFilterCap : 15) | 1;
     s.speckleWin = p.speckleWindowSize; s.speckleDiff = 16 * p.speckleRange;
+    if (c->sgbm_mode != 0 && c->sgbm_mode != 1) { set_error("sgbm_mode must be 0 (MODE_SGBM) or 1 (MODE_HH)"); return 1; }
+    s.mode = c->sgbm_mode;
     if (s.ftzero > 127) { set_error("preFilterCap too large"); return 1; }
     if (s.P1 < 0 || s.bs * s.bs * (2 * s.ftzero + 63) + s.P2 > 32767) {
         set_error("SGBM parameters leave the int16 cost domain OpenCV's result is pinned for (SURVEY.md A.4 validity domain)");
@@ -346,12 +348,12 @@ int ovo_knn2_hamming(ovo_ctx* c, const uint8_t* q, int nq, const uint8_t* t, int
 }
 
 int ovo_match_points(ovo_ctx* c, const int32_t* nn, int nq, double thr, const float* kp1, const float* kp2, const float* disp1,
-                     const float* disp2, int32_t* matches, float* pts1, float* pts2, int32_t* counts, void* stream) {
+                     const float* disp2, int32_t* matches, float* pts1, float* pts2, int32_t* counts, const int32_t* nn_rev, void* stream) {
     CHECK_CTX(c, 1);
     GatherParams p;
     memcpy(p.Q, c->cfg.Q, sizeof(p.Q));
     p.thr = thr; p.roi_x0 = c->L.x0; p.roi_y0 = c->L.y0; p.cw = c->L.cw; p.ch = c->L.ch; p.disp_pitch = c->L.cw;
-    return match_gather_launch(p, nn, nq, kp1, kp2, disp1, disp2, matches, pts1, pts2, counts, (cudaStream_t)stream);
+    return match_gather_launch(p, nn, nq, kp1, kp2, disp1, disp2, matches, pts1, pts2, counts, nn_rev, (cudaStream_t)stream);
 }
 
 int ovo_pair_batch(ovo_ctx* c, int n, const ovo_pair_item* items, double thr, void* stream) {

@@ -45,12 +45,13 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 struct SgbmDims {
     int W, H, D, Dp, W1;
     int bs, P1, P2, uniq, disp12, ftzero, speckleWin, speckleDiff;
+    int mode;  // 0 = MODE_SGBM (5 directions, what the reference uses); 1 = MODE_HH (8 directions, opt-in extension)
 };
 
 struct SgbmWorkspace {          // per frame, device pointers
     uint32_t* prep;             // [2 img][2 type][H][W]  byte-packed (v, vmin, vmax, 0)
     int16_t* C;                 // [H][W1][Dp] aggregated BT cost
-    int16_t* Lv;                // [3][H][W1][Dp] paths from (x-1,y-1), (x,y-1), (x+1,y-1); Lv[1] doubles as scratch
+    int16_t* Lv;                // [3 or 6][H][W1][Dp] paths from (x-1,y-1), (x,y-1), (x+1,y-1) (+ the three from row y+1 in MODE_HH); Lv[1] doubles as scratch
     int16_t* raw;               // [H][W] disparity after WTA + LR check
     int16_t* med;               // [H][W] after median
     int32_t* label;             // [H][W] speckle CCL labels
@@ -110,7 +111,7 @@ struct GatherParams {
 // pts1/pts2 [nq][3] f32, counts_out[0] = number of matches, counts_out[1] = lookups with no usable tap
 int match_gather_launch(const GatherParams& p, const int32_t* nn, int nq, const float* kp1, const float* kp2,
                         const float* disp1, const float* disp2, int32_t* matches_out, float* pts1, float* pts2,
-                        int32_t* counts_out, cudaStream_t st);
+                        int32_t* counts_out, const int32_t* nn_rev, cudaStream_t st);
 // Umeyama with OpenCV's scale leak.  m_dev: device count; out [16] f64: 3x4 [R|t], scale, angle,
 // |t|, flag(ok=1)
 int umeyama_launch(const float* pts1, const float* pts2, const int32_t* m_dev, int m_cap, double* out, cudaStream_t st);

@@ -131,6 +131,7 @@ struct PairItem {
     float *pts1, *pts2;
     double* out;        // [18]: 16 rigid-transform outputs, then two int32 counts in slot 16
     uint32_t* scratch;  // 2-NN partial results
+    int32_t* nn_rev;    // optional: 2-NN of the train set against the query set (cross-check), or null
 };
 constexpr int kMaxPairs = 16;
 struct PairBatch { PairItem it[kMaxPairs]; };
@@ -139,9 +140,10 @@ __global__ void __launch_bounds__(kKnnQ) k_knn2_partial(const uint8_t* __restric
                                                         int nsplit, uint32_t* __restrict__ part) {
     knn2_partial_body(q, nq, t, nt, nsplit, part);
 }
-__global__ void __launch_bounds__(kKnnQ) k_knn2_partial_b(PairBatch b, int nsplit) {
+__global__ void __launch_bounds__(kKnnQ) k_knn2_partial_b(PairBatch b, int nsplit, int reverse) {
     const PairItem& p = b.it[blockIdx.z];
-    knn2_partial_body(p.q, p.nq, p.t, p.nt, nsplit, p.scratch);
+    if (reverse) { if (p.nn_rev) knn2_partial_body(p.t, p.nt, p.q, p.nq, nsplit, p.scratch); }
+    else knn2_partial_body(p.q, p.nq, p.t, p.nt, nsplit, p.scratch);
 }
 
 __device__ __forceinline__ void knn2_merge_body(const uint32_t* __restrict__ part, int nq, int nsplit, int32_t* __restrict__ nn) {
@@ -163,9 +165,10 @@ __device__ __forceinline__ void knn2_merge_body(const uint32_t* __restrict__ par
 __global__ void k_knn2_merge(const uint32_t* __restrict__ part, int nq, int nsplit, int32_t* __restrict__ nn) {
     knn2_merge_body(part, nq, nsplit, nn);
 }
-__global__ void k_knn2_merge_b(PairBatch b, int nsplit) {
+__global__ void k_knn2_merge_b(PairBatch b, int nsplit, int reverse) {
     const PairItem& p = b.it[blockIdx.z];
-    knn2_merge_body(p.scratch, p.nq, nsplit, p.nn);
+    if (reverse) { if (p.nn_rev) knn2_merge_body(p.scratch, p.nt, nsplit, p.nn_rev); }
+    else knn2_merge_body(p.scratch, p.nq, nsplit, p.nn);
 }
 
 // ---- reprojection (A.5.1) ------------------------------------------------------------------------------------------------
@@ -228,7 +231,7 @@ __device__ __forceinline__ void match_gather_body(const GatherParams& P, const i
                                                   const float* __restrict__ kp1, const float* __restrict__ kp2,
                                                   const float* __restrict__ disp1, const float* __restrict__ disp2,
                                                   int32_t* __restrict__ matches, float* __restrict__ pts1, float* __restrict__ pts2,
-                                                  int32_t* __restrict__ counts) {
+                                                  int32_t* __restrict__ counts, const int32_t* __restrict__ nn_rev) {
     __shared__ int warp_sums[32];
     __shared__ int base_s, bad_s;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -243,6 +246,8 @@ __device__ __forceinline__ void match_gather_body(const GatherParams& P, const i
             ti = r.x; d0 = r.y;
             // m[0].distance < thr * m[1].distance evaluated in double (A.3)
             keep = r.x >= 0 && r.z >= 0 && (double)r.y < __dmul_rn(P.thr, (double)r.w);
+            // opt-in cross-check (not in the reference): the train descriptor's own nearest neighbour must be this query
+            if (keep && nn_rev != nullptr) keep = nn_rev[4 * (size_t)r.x] == qi;
         }
         const uint32_t bal = __ballot_sync(0xffffffffu, keep);
         const int wpre = __popc(bal & ((1u << lane) - 1));
@@ -279,12 +284,12 @@ __global__ void __launch_bounds__(1024) k_match_gather(GatherParams P, const int
                                                        const float* __restrict__ kp1, const float* __restrict__ kp2,
                                                        const float* __restrict__ disp1, const float* __restrict__ disp2,
                                                        int32_t* __restrict__ matches, float* __restrict__ pts1, float* __restrict__ pts2,
-                                                       int32_t* __restrict__ counts) {
-    match_gather_body(P, nn, nq, kp1, kp2, disp1, disp2, matches, pts1, pts2, counts);
+                                                       int32_t* __restrict__ counts, const int32_t* __restrict__ nn_rev) {
+    match_gather_body(P, nn, nq, kp1, kp2, disp1, disp2, matches, pts1, pts2, counts, nn_rev);
 }
 __global__ void __launch_bounds__(1024) k_match_gather_b(GatherParams P, PairBatch b) {
     const PairItem& p = b.it[blockIdx.x];
-    match_gather_body(P, p.nn, p.nq, p.kp1, p.kp2, p.disp1, p.disp2, p.matches, p.pts1, p.pts2, reinterpret_cast<int32_t*>(p.out + 16));
+    match_gather_body(P, p.nn, p.nq, p.kp1, p.kp2, p.disp1, p.disp2, p.matches, p.pts1, p.pts2, reinterpret_cast<int32_t*>(p.out + 16), p.nn_rev);
 }
 
 // ---- Umeyama (A.5.3) ---------------------------------------------------------------------------------------------------------
@@ -494,12 +499,22 @@ int pair_batch_launch(const GatherParams& gp, int n, const void* items_host, int
         maxt = b.it[i].nt > maxt ? b.it[i].nt : maxt;
         if (b.it[i].nt >= (1 << 20)) { set_error("knn2: train set too large"); return 1; }
     }
+    bool any_rev = false;
+    for (int i = 0; i < n; i++) any_rev = any_rev || b.it[i].nn_rev != nullptr;
+    if (any_rev && maxt > 0) {  // cross-check: train -> query 2-NN first (shares the scratch with the forward pass)
+        int nsplit = cdiv(maxq, 128);
+        nsplit = nsplit < 1 ? 1 : (nsplit > 32 ? 32 : nsplit);
+        OVO_LAUNCH(k_knn2_partial_b, dim3(cdiv(maxt, kKnnQ), nsplit, n), dim3(kKnnQ), 0, st, b, nsplit, 1);
+        OVO_LAUNCH_CHECK();
+        OVO_LAUNCH(k_knn2_merge_b, dim3(cdiv(maxt, 128), 1, n), dim3(128), 0, st, b, nsplit, 1);
+        OVO_LAUNCH_CHECK();
+    }
     if (maxq > 0) {
         int nsplit = cdiv(maxt, 128);
         nsplit = nsplit < 1 ? 1 : (nsplit > 32 ? 32 : nsplit);
-        OVO_LAUNCH(k_knn2_partial_b, dim3(cdiv(maxq, kKnnQ), nsplit, n), dim3(kKnnQ), 0, st, b, nsplit);
+        OVO_LAUNCH(k_knn2_partial_b, dim3(cdiv(maxq, kKnnQ), nsplit, n), dim3(kKnnQ), 0, st, b, nsplit, 0);
         OVO_LAUNCH_CHECK();
-        OVO_LAUNCH(k_knn2_merge_b, dim3(cdiv(maxq, 128), 1, n), dim3(128), 0, st, b, nsplit);
+        OVO_LAUNCH(k_knn2_merge_b, dim3(cdiv(maxq, 128), 1, n), dim3(128), 0, st, b, nsplit, 0);
         OVO_LAUNCH_CHECK();
     }
     OVO_LAUNCH(k_match_gather_b, dim3(n), dim3(1024), 0, st, gp, b);
@@ -512,8 +527,9 @@ int pair_item_size() { return (int)sizeof(PairItem); }
 int pair_max_batch() { return kMaxPairs; }
 
 int match_gather_launch(const GatherParams& p, const int32_t* nn, int nq, const float* kp1, const float* kp2, const float* disp1,
-                        const float* disp2, int32_t* matches_out, float* pts1, float* pts2, int32_t* counts_out, cudaStream_t st) {
-    OVO_LAUNCH(k_match_gather, dim3(1), dim3(1024), 0, st, p, nn, nq, kp1, kp2, disp1, disp2, matches_out, pts1, pts2, counts_out);
+                        const float* disp2, int32_t* matches_out, float* pts1, float* pts2, int32_t* counts_out, const int32_t* nn_rev,
+                        cudaStream_t st) {
+    OVO_LAUNCH(k_match_gather, dim3(1), dim3(1024), 0, st, p, nn, nq, kp1, kp2, disp1, disp2, matches_out, pts1, pts2, counts_out, nn_rev);
     OVO_LAUNCH_CHECK();
     return 0;
 }

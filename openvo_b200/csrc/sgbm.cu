@@ -248,7 +248,7 @@ __device__ __forceinline__ void stv(uint32_t* p, const uint32_t (&v)[NPR]) {
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kVertPF = 8;
 
-template <int NPR, bool PAD, int DIR>
+template <int NPR, bool PAD, int DIR, bool UP>
 __device__ __forceinline__ void vert_line(const SgbmDims& d, const uint32_t* __restrict__ C, uint32_t* __restrict__ Lout, int line,
                                           int lane) {
     constexpr int WPC = 32 * NPR;  // words per cell
@@ -256,9 +256,10 @@ __device__ __forceinline__ void vert_line(const SgbmDims& d, const uint32_t* __r
     const int W1 = d.W1, H = d.H;
     const int xreset = DIR == 0 ? 0 : (DIR == 2 ? W1 - 1 : -1);
     const ptrdiff_t rowstride = (ptrdiff_t)W1 * WPC;
+    const ptrdiff_t rowadv = UP ? -rowstride : rowstride;  // UP: MODE_HH's second pass walks the rows bottom -> top
     // pointer / column of the next row of this scan line (wraps around the image, which is where the path restarts)
     auto next_row = [&](int& x, auto*& p) {
-        p += rowstride + STEP * WPC;
+        p += rowadv + STEP * WPC;
         if (STEP != 0) {
             x += STEP;
             if (STEP > 0 && x == W1) { x = 0; p -= rowstride; }
@@ -272,8 +273,9 @@ __device__ __forceinline__ void vert_line(const SgbmDims& d, const uint32_t* __r
 
     uint32_t cbuf[kVertPF][NPR];
     int xpf = line, x = line;
-    const uint32_t* ppf = C + (size_t)line * WPC;
-    uint32_t* pl = Lout + (size_t)line * WPC;
+    const size_t row0 = UP ? (size_t)(H - 1) * rowstride : 0;
+    const uint32_t* ppf = C + row0 + (size_t)line * WPC;
+    uint32_t* pl = Lout + row0 + (size_t)line * WPC;
 #pragma unroll
     for (int i = 0; i < kVertPF; i++) {
         if (i < H) ldv<NPR>(cbuf[i], ppf);
@@ -319,14 +321,18 @@ __global__ void __launch_bounds__(256) k_sgbm_vert(SgbmDims d, SgbmWorkspace ws,
     const int lane = threadIdx.x & 31;
     // direction is the fastest-varying block coordinate: the three directions of the same columns are resident together and
     // share their reads of C through L2
-    const int dir = blockIdx.x % 3, f = blockIdx.y;
-    const int line = (blockIdx.x / 3) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int ndir = d.mode ? 6 : 3;
+    const int dir = blockIdx.x % ndir, f = blockIdx.y;
+    const int line = (blockIdx.x / ndir) * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (line >= d.W1) return;
     const uint32_t* C = reinterpret_cast<const uint32_t*>(frame_ptr(ws.C, ws_stride, f)) + lane * NPR;
     uint32_t* Lout = reinterpret_cast<uint32_t*>(frame_ptr(ws.Lv, ws_stride, f)) + (size_t)dir * d.H * d.W1 * (32 * NPR) + lane * NPR;
-    if (dir == 0) vert_line<NPR, PAD, 0>(d, C, Lout, line, lane);
-    else if (dir == 1) vert_line<NPR, PAD, 1>(d, C, Lout, line, lane);
-    else vert_line<NPR, PAD, 2>(d, C, Lout, line, lane);
+    if (dir == 0) vert_line<NPR, PAD, 0, false>(d, C, Lout, line, lane);
+    else if (dir == 1) vert_line<NPR, PAD, 1, false>(d, C, Lout, line, lane);
+    else if (dir == 2) vert_line<NPR, PAD, 2, false>(d, C, Lout, line, lane);
+    else if (dir == 3) vert_line<NPR, PAD, 0, true>(d, C, Lout, line, lane);   // from (x-1, y+1)
+    else if (dir == 4) vert_line<NPR, PAD, 1, true>(d, C, Lout, line, lane);   // from (x,   y+1)
+    else vert_line<NPR, PAD, 2, true>(d, C, Lout, line, lane);                 // from (x+1, y+1)
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -450,12 +456,24 @@ __global__ void __launch_bounds__(64, OVO_HOR_MINB) k_sgbm_horiz(SgbmDims d, Sgb
             if (i < n1) { ldv<NPR>(cb[i], pc); ldv<NPR>(l1[i], p1); ldv<NPR>(l2[i], p2); ldv<NPR>(l3[i], p3); }
             pc += dstep; p1 += dstep; p2 += dstep; p3 += dstep;
         }
+        const bool hh = d.mode != 0;  // MODE_HH: add the three bottom-up paths Lv[3..5] (read late, not prefetched)
+        const uint32_t* pu = L1 + 3 * vol + xa * WPC;
         auto body = [&](int i, bool pf) {
             uint32_t c[NPR], sv[NPR];
 #pragma unroll
             for (int r = 0; r < NPR; r++) {
                 c[r] = cb[i][r];
                 sv[r] = __viaddmin_u16x2(__viaddmin_u16x2(l1[i][r], l2[i][r], kMaxC2), l3[i][r], kMaxC2);
+            }
+            if (hh) {
+#pragma unroll
+                for (int v = 0; v < 3; v++) {
+                    uint32_t u[NPR];
+                    ldv<NPR>(u, pu + (size_t)v * vol);
+#pragma unroll
+                    for (int r = 0; r < NPR; r++) sv[r] = __viaddmin_u16x2(sv[r], u[r], kMaxC2);
+                }
+                pu += dstep;
             }
             if (pf) { ldv<NPR>(cb[i], pc); ldv<NPR>(l1[i], p1); ldv<NPR>(l2[i], p2); ldv<NPR>(l3[i], p3); }
             pc += dstep; p1 += dstep; p2 += dstep; p3 += dstep;
@@ -669,7 +687,7 @@ __global__ void k_ccl_apply(const int16_t* __restrict__ img, const int32_t* __re
 
 template <int NPR, bool PAD>
 int launch_paths(const SgbmDims& d, const SgbmWorkspace& ws, size_t ws_stride, int nb, cudaStream_t st) {
-    dim3 gv(3 * cdiv(d.W1, 8), nb);
+    dim3 gv((d.mode ? 6 : 3) * cdiv(d.W1, 8), nb);
     { auto k_sgbm_vert_t = k_sgbm_vert<NPR, PAD>; OVO_LAUNCH(k_sgbm_vert_t, gv, dim3(256), 0, st, d, ws, ws_stride); }
     OVO_LAUNCH_CHECK();
     dim3 gh(d.H, nb);
@@ -696,7 +714,7 @@ int launch_cost(const SgbmDims& d, const SgbmWorkspace& ws, size_t ws_stride, in
 size_t sgbm_workspace_bytes(const SgbmDims& d) {
     const size_t vol = align_up((size_t)d.H * d.W1 * d.Dp * 2, 256);
     const size_t img = align_up((size_t)d.H * d.W * 4, 256);
-    return align_up(4 * img /*prep*/ + 4 * vol /*C + Lv[3]*/ + 4 * img /*raw, med (i16) + label, csize (i32) -> 2*0.5+2 = 3 img*/, 256);
+    return align_up(4 * img /*prep*/ + (d.mode ? 7 : 4) * vol /*C + Lv[3]*/ + 4 * img /*raw, med (i16) + label, csize (i32) -> 2*0.5+2 = 3 img*/, 256);
 }
 
 void sgbm_carve(const SgbmDims& d, uint8_t* base, SgbmWorkspace* ws) {
@@ -705,7 +723,7 @@ void sgbm_carve(const SgbmDims& d, uint8_t* base, SgbmWorkspace* ws) {
     uint8_t* p = base;
     ws->prep = reinterpret_cast<uint32_t*>(p); p += 4 * img;
     ws->C = reinterpret_cast<int16_t*>(p); p += vol;
-    ws->Lv = reinterpret_cast<int16_t*>(p); p += 3 * vol;
+    ws->Lv = reinterpret_cast<int16_t*>(p); p += (d.mode ? 6 : 3) * vol;
     ws->raw = reinterpret_cast<int16_t*>(p); p += img / 2;
     ws->med = reinterpret_cast<int16_t*>(p); p += img / 2;
     ws->label = reinterpret_cast<int32_t*>(p); p += img;

@@ -46,6 +46,7 @@ class Engine:
         # persistent buffers of the pair step, one slot per frame of the batch
         nb = self.max_batch
         self.nn = torch.empty((nb, self.kp_cap, 4), dtype=torch.int32, device=self.device)
+        self.nn_rev = torch.empty((nb, self.kp_cap, 4), dtype=torch.int32, device=self.device)  # cross-check (opt-in)
         self.matches = torch.empty((nb, self.kp_cap, 3), dtype=torch.int32, device=self.device)
         self.pts1 = torch.empty((nb, self.kp_cap, 3), dtype=torch.float32, device=self.device)
         self.pts2 = torch.empty((nb, self.kp_cap, 3), dtype=torch.float32, device=self.device)
@@ -164,7 +165,10 @@ class Engine:
         N.check(self.lib, self.lib.ovo_knn2_hamming(self.ctx, desc_q.data_ptr(), nq, desc_t.data_ptr(), nt, nn.data_ptr(), self._stream()))
         return nn
 
-    def pair_async(self, a, b, match_threshold, slot=0):
+    def pair_async(self, a, b, match_threshold, slot=0, cross_check=False):
+        return self.pair_batch_async([(a, b, slot)], match_threshold, cross_check)
+
+    def _pair_async_seams(self, a, b, match_threshold, slot=0):
         """Frames a (query) and b (train): 2-NN + ratio + fused 3-D lookup + rigid alignment, all on the device; results
         land in pair_out[slot].  Nothing is read back until pair_collect()."""
         st = self._stream()
@@ -174,11 +178,11 @@ class Engine:
         N.check(self.lib, self.lib.ovo_match_points(self.ctx, nn.data_ptr(), a.n_kp, float(match_threshold), a.kp.data_ptr(),
                                                     b.kp.data_ptr(), a.disp.data_ptr(), b.disp.data_ptr(),
                                                     self.matches[slot].data_ptr(), self.pts1[slot].data_ptr(),
-                                                    self.pts2[slot].data_ptr(), counts_ptr, st))
+                                                    self.pts2[slot].data_ptr(), counts_ptr, None, st))
         N.check(self.lib, self.lib.ovo_rigid_transform(self.ctx, self.pts1[slot].data_ptr(), self.pts2[slot].data_ptr(), counts_ptr,
                                                        self.kp_cap, out.data_ptr(), st))
 
-    def pair_batch_async(self, jobs, match_threshold):
+    def pair_batch_async(self, jobs, match_threshold, cross_check=False):
         """jobs: list of (frame a, frame b, slot).  All pairs in four launches (ovo_pair_batch); results land in pair_out[slot]."""
         if not jobs:
             return
@@ -188,6 +192,7 @@ class Engine:
             it.kp1, it.kp2, it.disp1, it.disp2 = a.kp.data_ptr(), b.kp.data_ptr(), a.disp.data_ptr(), b.disp.data_ptr()
             it.nn, it.matches = self.nn[slot].data_ptr(), self.matches[slot].data_ptr()
             it.pts1, it.pts2, it.out = self.pts1[slot].data_ptr(), self.pts2[slot].data_ptr(), self.pair_out[slot].data_ptr()
+            it.nn_rev = self.nn_rev[slot].data_ptr() if cross_check else None
         N.check(self.lib, self.lib.ovo_pair_batch(self.ctx, len(jobs), items, float(match_threshold), self._stream()))
 
     def pair_collect(self, nslots=1):
@@ -202,8 +207,8 @@ class Engine:
             res.append((int(counts[0]), int(counts[1]), host[s, :16].copy()))
         return res
 
-    def pair(self, a, b, match_threshold):
-        self.pair_async(a, b, match_threshold, 0)
+    def pair(self, a, b, match_threshold, cross_check=False):
+        self.pair_async(a, b, match_threshold, 0, cross_check)
         return self.pair_collect(1)[0]
 
     def filtered_transform(self, pts1, pts2, count_dev, rigidity_threshold, outlier_threshold, min_matches):

@@ -41,7 +41,7 @@ class _SgbmHandle:
             if key in p:
                 return lambda: p[key]
             if key == "mode":
-                return lambda: 0  # MODE_SGBM
+                return lambda: p.get("mode", 0)
         raise AttributeError(name)
 
 
@@ -64,6 +64,8 @@ class StereoCamera:
         self.map_right_1, self.map_right_2 = cv2.initUndistortRectifyMap(K_right, dist_right, R2, P2, img_size, cv2.CV_16SC2)
         self.img_size = (int(img_size[0]), int(img_size[1]))
         self.sgbm_params = {k: int(sgbm_params[k]) for k in N.SGBM_KEYS}
+        # opt-in extension (not in the reference, whose `mode=1` is commented out at stereo_camera.py:27): 'mode': 1 -> MODE_HH
+        self.sgbm_params["mode"] = int(sgbm_params.get("mode", 0))
         self.stereoSGBM = _SgbmHandle(self)
         self._engines = {}
 

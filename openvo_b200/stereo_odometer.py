@@ -78,7 +78,7 @@ class StereoOdometer:
     MAX_ROTATION_CHANGE = np.pi / 3
 
     def __init__(self, stereo_camera, nfeatures=500, match_threshold=0.8, rigidity_threshold=0, outlier_threshold=0,
-                 preprocessed_frames=False, min_matches=10, _max_batch=1, _engine_tag=0):
+                 preprocessed_frames=False, min_matches=10, cross_check=False, _max_batch=1, _engine_tag=0):
         self.stereo = stereo_camera
         self._nfeatures = nfeatures
         self._max_batch = _max_batch  # >1 only when driven by openvo_b200.batch.BatchOdometer
@@ -89,6 +89,8 @@ class StereoOdometer:
         self.match_threshold, self.rigidity_threshold = match_threshold, rigidity_threshold
         self.outlier_threshold, self.preprocessed_frames = outlier_threshold, preprocessed_frames
         self.min_matches = min_matches
+        # opt-in extension: left-right cross-check of the matches (the reference's "TODO crosscheck", stereo_odometer.py:21)
+        self.cross_check = cross_check
         self.skipped_frames = 0
         self.c_T_w = np.eye(4)
         self.c_T_w_prev = np.eye(4)
@@ -209,7 +211,7 @@ class StereoOdometer:
             raise IndexError("tuple index out of range")  # the reference indexes m[1] (ref: stereo_odometer.py:164)
         slot = 0
         if result is None:
-            n, bad, out = eng.pair(a, b, self.match_threshold)
+            n, bad, out = eng.pair(a, b, self.match_threshold, self.cross_check)
         else:
             slot, (n, bad, out) = result
         self.last_match_count = n

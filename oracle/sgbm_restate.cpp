@@ -148,6 +148,12 @@ extern "C" {
 //   raw_out      : int16 [H][W] disparity after LR check, before median/speckle
 //   med_out      : int16 [H][W] after the 3x3 median, before the speckle filter
 // Returns 0, or 1 if the parameters leave the pinned validity domain (A.4 "Validity domain").
+static int sgbm_hh(const uint8_t* L, const uint8_t* R, const SgbmP& p, int16_t* disp_out);
+
+int orc_sgbm_compute_mode(const uint8_t* L, const uint8_t* R, int W, int H, int minDisparity, int numDisparities,
+                          int blockSize, int P1, int P2, int disp12MaxDiff, int preFilterCap, int uniquenessRatio,
+                          int speckleWindowSize, int speckleRange, int mode, int16_t* disp_out);
+
 int orc_sgbm_compute(const uint8_t* L, const uint8_t* R, int W, int H, int minDisparity, int numDisparities,
                      int blockSize, int P1, int P2, int disp12MaxDiff, int preFilterCap, int uniquenessRatio,
                      int speckleWindowSize, int speckleRange, int16_t* disp_out, int16_t* C_out, int16_t* S_out,
@@ -255,4 +261,113 @@ int orc_sgbm_compute(const uint8_t* L, const uint8_t* R, int W, int H, int minDi
     return 0;
 }
 
+// mode 0 = MODE_SGBM (what the reference uses), 1 = MODE_HH (8 paths, two passes over stored C / S volumes; SURVEY.md A.4 end;
+// NOT used by the reference — opt-in extension row n4, pinned against cv2's own MODE_HH)
+int orc_sgbm_compute_mode(const uint8_t* L, const uint8_t* R, int W, int H, int minDisparity, int numDisparities,
+                          int blockSize, int P1, int P2, int disp12MaxDiff, int preFilterCap, int uniquenessRatio,
+                          int speckleWindowSize, int speckleRange, int mode, int16_t* disp_out) {
+    if (mode == 0)
+        return orc_sgbm_compute(L, R, W, H, minDisparity, numDisparities, blockSize, P1, P2, disp12MaxDiff, preFilterCap,
+                                uniquenessRatio, speckleWindowSize, speckleRange, disp_out, nullptr, nullptr, nullptr, nullptr);
+    SgbmP p;
+    p.W = W; p.H = H; p.D = numDisparities; p.bs = blockSize; p.P1 = P1;
+    p.P2 = std::max(P2, P1 + 1);
+    p.uniq = uniquenessRatio;
+    p.disp12 = disp12MaxDiff > 0 ? disp12MaxDiff : 1;
+    p.ftzero = std::max(preFilterCap, 15) | 1;
+    p.speckleWin = speckleWindowSize; p.speckleRange = speckleRange;
+    if (minDisparity != 0 || p.D <= 0 || p.D % 16 || W <= p.D || blockSize < 1 || !(blockSize & 1)) return 1;
+    if (blockSize * blockSize * (2 * p.ftzero + 63) + p.P2 > 32767) return 1;
+    return sgbm_hh(L, R, p, disp_out);
+}
+
 }  // extern "C"
+
+static int sgbm_hh(const uint8_t* L, const uint8_t* R, const SgbmP& p, int16_t* disp_out) {
+    const int W = p.W, H = p.H, D = p.D, W1 = W - D, SW2 = p.bs / 2, SH2 = p.bs / 2;
+    const int INV = -16, MAXC = 32767;
+    const size_t rowsz = (size_t)W1 * D;
+    std::vector<std::vector<int16_t>> hs(H);
+    {
+        std::vector<int16_t> pix;
+        for (int y = 0; y < H; y++) {
+            pix_row(L, R, p, y, pix);
+            hs[y].assign(rowsz, 0);
+            for (int x1 = 0; x1 < W1; x1++)
+                for (int dx = -SW2; dx <= SW2; dx++) {
+                    const int16_t* s = &pix[(size_t)clampi(x1 + dx, 0, W1 - 1) * D];
+                    int16_t* o = &hs[y][(size_t)x1 * D];
+                    for (int d = 0; d < D; d++) o[d] += s[d];
+                }
+        }
+    }
+    std::vector<int16_t> C((size_t)H * rowsz, 0), S((size_t)H * rowsz, 0);
+    for (int y = 0; y < H; y++)
+        for (int dy = -SH2; dy <= SH2; dy++) {
+            const std::vector<int16_t>& h = hs[clampi(y + dy, 0, H - 1)];
+            int16_t* c = &C[(size_t)y * rowsz];
+            for (size_t i = 0; i < rowsz; i++) c[i] += h[i];
+        }
+    hs.clear();
+    std::vector<int16_t> disp1((size_t)W * H, (int16_t)INV);
+    std::vector<int> disp2(W), disp2cost(W);
+    for (int pass = 0; pass < 2; pass++) {
+        const int y0 = pass == 0 ? 0 : H - 1, y1 = pass == 0 ? H : -1, dy = pass == 0 ? 1 : -1;
+        const int x0 = pass == 0 ? 0 : W1 - 1, x1e = pass == 0 ? W1 : -1, dx = pass == 0 ? 1 : -1;
+        std::vector<int16_t> Lprev[3], Lcur[3], L0(rowsz);
+        for (int r = 0; r < 3; r++) { Lprev[r].assign(rowsz, 0); Lcur[r].assign(rowsz, 0); }
+        for (int y = y0; y != y1; y += dy) {
+            const int16_t* Crow = &C[(size_t)y * rowsz];
+            int16_t* Srow = &S[(size_t)y * rowsz];
+            const bool have_prev_row = y != y0;
+            if (pass == 1) for (int x = 0; x < W; x++) { disp2[x] = INV; disp2cost[x] = MAXC; }
+            for (int x1 = x0; x1 != x1e; x1 += dx) {
+                const int16_t* Cc = &Crow[(size_t)x1 * D];
+                const int xp = x1 - dx, xn = x1 + dx;  // previous / next column in sweep order
+                const bool in_p = xp >= 0 && xp < W1, in_n = xn >= 0 && xn < W1;
+                path_step(Cc, in_p ? &L0[(size_t)xp * D] : nullptr, &L0[(size_t)x1 * D], D, p.P1, p.P2, in_p);
+                path_step(Cc, (in_p && have_prev_row) ? &Lprev[0][(size_t)xp * D] : nullptr, &Lcur[0][(size_t)x1 * D], D, p.P1, p.P2, in_p && have_prev_row);
+                path_step(Cc, have_prev_row ? &Lprev[1][(size_t)x1 * D] : nullptr, &Lcur[1][(size_t)x1 * D], D, p.P1, p.P2, have_prev_row);
+                path_step(Cc, (in_n && have_prev_row) ? &Lprev[2][(size_t)xn * D] : nullptr, &Lcur[2][(size_t)x1 * D], D, p.P1, p.P2, in_n && have_prev_row);
+                int16_t* Sc = &Srow[(size_t)x1 * D];
+                int best = 0, minS = MAXC + 1;
+                for (int d = 0; d < D; d++) {
+                    size_t i = (size_t)x1 * D + d;
+                    Sc[d] = sat16((int)Sc[d] + L0[i] + Lcur[0][i] + Lcur[1][i] + Lcur[2][i]);
+                    if (Sc[d] < minS) { minS = Sc[d]; best = d; }
+                }
+                if (pass == 0) continue;
+                bool uniq_ok = true;
+                for (int d = 0; d < D; d++)
+                    if (Sc[d] * (100 - p.uniq) < minS * 100 && std::abs(best - d) > 1) { uniq_ok = false; break; }
+                if (!uniq_ok) continue;
+                int x = x1 + D, x2 = x - best;
+                if (disp2cost[x2] > minS) { disp2cost[x2] = minS; disp2[x2] = best; }
+                int dsp;
+                if (best > 0 && best < D - 1) {
+                    int den = std::max(Sc[best - 1] + Sc[best + 1] - 2 * Sc[best], 1);
+                    dsp = best * 16 + ((Sc[best - 1] - Sc[best + 1]) * 16 + den) / (2 * den);
+                } else dsp = best * 16;
+                disp1[(size_t)y * W + x] = (int16_t)dsp;
+            }
+            for (int r = 0; r < 3; r++) std::swap(Lprev[r], Lcur[r]);
+            if (pass == 1) {
+                int16_t* d1row = &disp1[(size_t)y * W];
+                for (int x = D; x < W; x++) {
+                    int d1 = d1row[x];
+                    if (d1 == INV) continue;
+                    int _d = d1 >> 4, d_ = (d1 + 15) >> 4;
+                    int _x = x - _d, x_ = x - d_;
+                    if (0 <= _x && _x < W && disp2[_x] >= 0 && std::abs(disp2[_x] - _d) > p.disp12 &&
+                        0 <= x_ && x_ < W && disp2[x_] >= 0 && std::abs(disp2[x_] - d_) > p.disp12)
+                        d1row[x] = (int16_t)INV;
+                }
+            }
+        }
+    }
+    std::vector<int16_t> med((size_t)W * H);
+    median3(disp1.data(), med.data(), W, H);
+    if (p.speckleWin > 0) speckles(med.data(), W, H, INV, p.speckleWin, 16 * p.speckleRange);
+    memcpy(disp_out, med.data(), (size_t)W * H * 2);
+    return 0;
+}

@@ -117,7 +117,7 @@ def test_match_and_pose_kernels(emu):
     N.check(emu, emu.ovo_knn2_hamming(c.ctx, N.ptr(q), nq, N.ptr(t), nt, N.ptr(nn), None))
     matches, p1, p2, cnt = np.zeros((nq, 3), np.int32), np.zeros((nq, 3), np.float32), np.zeros((nq, 3), np.float32), np.zeros(2, np.int32)
     N.check(emu, emu.ovo_match_points(c.ctx, N.ptr(nn), nq, 0.8, N.ptr(kp1), N.ptr(kp2), N.ptr(df), N.ptr(df), N.ptr(matches),
-                                     N.ptr(p1), N.ptr(p2), N.ptr(cnt), None))
+                                     N.ptr(p1), N.ptr(p2), N.ptr(cnt), None, None))
     keep = [i for i in range(nq) if float(nn[i, 1]) < 0.8 * float(nn[i, 3])]
     assert cnt[0] == len(keep) >= 90 and np.array_equal(matches[:cnt[0], 0], keep)
     with np.errstate(all="ignore"):
@@ -147,7 +147,7 @@ def test_match_and_pose_kernels(emu):
         assert np.array_equal(nn1, bufs["nn"])
         m1, a1, b1, c1 = np.zeros((len(qq), 3), np.int32), np.zeros((len(qq), 3), np.float32), np.zeros((len(qq), 3), np.float32), np.zeros(2, np.int32)
         N.check(emu, emu.ovo_match_points(c.ctx, N.ptr(nn1), len(qq), 0.8, N.ptr(bufs["ka"]), N.ptr(bufs["kb"]), N.ptr(df), N.ptr(df),
-                                         N.ptr(m1), N.ptr(a1), N.ptr(b1), N.ptr(c1), None))
+                                         N.ptr(m1), N.ptr(a1), N.ptr(b1), N.ptr(c1), None, None))
         cnt_b = bufs["out"][16:17].view(np.int32)
         assert cnt_b[0] == c1[0] and cnt_b[1] == c1[1]
         k = c1[0]
@@ -155,6 +155,22 @@ def test_match_and_pose_kernels(emu):
         o1 = np.zeros(16)
         N.check(emu, emu.ovo_rigid_transform(c.ctx, N.ptr(a1), N.ptr(b1), N.ptr(c1), c.cap, N.ptr(o1), None))
         assert np.array_equal(o1, bufs["out"][:16], equal_nan=True)
+    # opt-in cross-check: batched pair step with nn_rev == forward matches filtered by mutual nearest neighbours (cv2 tie rule)
+    items2 = (N.PairItem * 1)()
+    b0 = keepers[0]
+    rev = np.zeros((len(b0["t"]), 4), np.int32)
+    out2, m2 = np.zeros(18), np.zeros((len(b0["q"]), 3), np.int32)
+    it = items2[0]
+    it.q_desc, it.t_desc, it.nq, it.nt = N.ptr(b0["q"]), N.ptr(b0["t"]), len(b0["q"]), len(b0["t"])
+    it.kp1, it.kp2, it.disp1, it.disp2 = N.ptr(b0["ka"]), N.ptr(b0["kb"]), N.ptr(df), N.ptr(df)
+    it.nn, it.matches, it.pts1, it.pts2, it.out = N.ptr(b0["nn"]), N.ptr(m2), N.ptr(b0["p1"]), N.ptr(b0["p2"]), N.ptr(out2)
+    it.nn_rev = N.ptr(rev)
+    N.check(emu, emu.ovo_pair_batch(c2.ctx, 1, items2, 0.8, None))
+    assert np.array_equal(rev, O.knn2_hamming(b0["t"], b0["q"]))
+    fwd = O.knn2_hamming(b0["q"], b0["t"])
+    want = [i for i in range(len(fwd)) if float(fwd[i, 1]) < 0.8 * float(fwd[i, 3]) and rev[fwd[i, 0], 0] == i]
+    k2 = int(out2[16:17].view(np.int32)[0])
+    assert k2 == len(want) and np.array_equal(m2[:k2, 0], want) and 0 < k2 <= cnt_b[0] + 1000
     # Umeyama
     src = rng.normal(0, 5, (150, 3)).astype(np.float32)
     ang = 0.04
@@ -227,3 +243,17 @@ def test_pose_filter_kernels(emu):
     N.check(emu, emu.ovo_outlier_filter(c.ctx, N.ptr(a), N.ptr(b), N.ptr(cnt), c.cap, N.ptr(Tdev), 0.02, None))
     assert cnt[0] == keep.sum() and 0 < keep.sum() < k
     assert np.array_equal(a[:cnt[0]], p[keep]) and np.array_equal(b[:cnt[0]], q[keep])
+
+
+def test_sgbm_mode_hh_kernels(emu):
+    """opt-in 8-direction MODE_HH vs its oracle restatement (which is pinned to cv2's MODE_HH)."""
+    W, H, D = 160, 40, 32
+    p = sgbm_params(D)
+    p["mode"] = 1
+    L, R = occluded_pair(W, H)
+    c = Ctx(emu, W, H, p, (0, 0, W, H), np.eye(4), 100)
+    out = np.zeros((1, H, W), np.int16)
+    N.check(emu, emu.ovo_sgbm_compute(c.ctx, N.ptr(L), N.ptr(R), W, W * H, 1, N.ptr(out), None))
+    ref = O.sgbm_compute_mode(L, R, p, 1)
+    assert np.array_equal(out[0], ref)
+    assert (ref != O.sgbm_compute(L, R, p)).sum() > 0  # and it is a different result from the reference's MODE_SGBM

@@ -240,3 +240,35 @@ def test_frame_chunk_sharding_equals_sequential(golden):
         sall[start:start + len(st)] = st
     chain = D.replay_chains(Tall[None], sall[None])[0]
     assert _pose_close(chain, g["cTw_%d" % (nfr - 1)])
+
+
+@pytest.mark.parametrize("W,H,D", [(200, 60, 32), (320, 96, 64), (1241, 376, 128)])
+def test_sgbm_mode_hh_opt_in(W, H, D):
+    # extension row n4 (not the reference's behaviour): 8-direction MODE_HH, bit-exact vs the oracle restatement / cv2's MODE_HH
+    args = synth.camera_args(W, H, D)
+    args["sgbm_params"]["mode"] = 1
+    cam = StereoCamera(**args)
+    L, R = occluded_pair(W, H, d=min(24, D // 2))
+    got = cam.stereoSGBM.compute(L, R)
+    assert np.array_equal(got, O.sgbm_compute_mode(L, R, args["sgbm_params"], 1))
+    cv2 = pytest.importorskip("cv2")
+    p = args["sgbm_params"]
+    ref = cv2.StereoSGBM_create(*[p[k] for k in O.SGBM_KEYS], mode=cv2.STEREO_SGBM_MODE_HH).compute(L, R)
+    assert np.array_equal(got, ref)
+
+
+def test_cross_check_opt_in(golden):
+    # extension row n4: left-right cross-check of the matches (the reference's "TODO crosscheck"); default stays off
+    g = golden("seq_small")
+    W, H, D, n = int(g["W"]), int(g["H"]), int(g["D"]), int(g["nfeatures"])
+    cam, _ = _cam(W, H, D)
+    od = StereoOdometer(cam, nfeatures=n, preprocessed_frames=True, cross_check=True)
+    plain = StereoOdometer(cam, nfeatures=n, preprocessed_frames=True)
+    for i in range(2):
+        assert od.update(g["left"][i], g["right"][i]) and plain.update(g["left"][i], g["right"][i])
+    fwd = O.knn2_hamming(g["desc_0"], g["desc_1"])
+    rev = O.knn2_hamming(g["desc_1"], g["desc_0"])
+    want = [i for i in range(len(fwd)) if float(fwd[i, 1]) < 0.8 * float(fwd[i, 3]) and rev[fwd[i, 0], 0] == i]
+    eng = od._engine()
+    assert od.last_match_count == len(want) < plain.last_match_count
+    assert np.array_equal(eng.matches[0, :len(want), 0].cpu().numpy(), want)

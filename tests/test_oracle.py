@@ -174,3 +174,12 @@ def test_port_equals_live_reference():
         assert np.array_equal(ref.current_disparity, port.cur[1]) and np.array_equal(ref.current_desc, port.cur[4])
         assert np.array_equal(ref.current_3d.view(np.uint32), port.cur[2].view(np.uint32))
         assert np.abs(ref.c_T_w - port.c_T_w).max() < 1e-9
+
+
+def test_sgbm_mode_hh_restated_equals_cv2():
+    # extension row n4: 8-direction MODE_HH (not used by the reference) pinned against cv2's own implementation
+    for W, H, D, kw in SGBM_CASES[:3]:
+        L, R = occluded_pair(W, H)
+        p = sgbm_params(D, **kw)
+        ref = cv2.StereoSGBM_create(*[p[k] for k in O.SGBM_KEYS], mode=cv2.STEREO_SGBM_MODE_HH).compute(L, R)
+        assert np.array_equal(O.sgbm_compute_mode(L, R, p, 1), ref)
