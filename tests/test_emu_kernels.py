@@ -257,3 +257,20 @@ def test_sgbm_mode_hh_kernels(emu):
     ref = O.sgbm_compute_mode(L, R, p, 1)
     assert np.array_equal(out[0], ref)
     assert (ref != O.sgbm_compute(L, R, p)).sum() > 0  # and it is a different result from the reference's MODE_SGBM
+
+
+def test_sgbm_kernels_random_small(emu):
+    rng = np.random.default_rng(5)
+    for trial in range(4):
+        D = int(rng.choice([16, 48, 80]))
+        W, H = D + int(rng.integers(17, 60)), int(rng.integers(16, 30))
+        bs = int(rng.choice([3, 5, 9]))
+        kw = dict(blockSize=bs, P1=8 * bs, P2=8 * bs + int(rng.integers(1, 300)), disp12MaxDiff=int(rng.choice([-1, 1, 3])),
+                  preFilterCap=int(rng.choice([1, 31, 63])), uniquenessRatio=int(rng.choice([0, 10, 40])),
+                  speckleWindowSize=int(rng.choice([0, 30])), speckleRange=2)
+        p = sgbm_params(D, **kw)
+        L, R = occluded_pair(W, H, d=5)
+        c = Ctx(emu, W, H, p, (0, 0, W, H), np.eye(4), 100)
+        out = np.zeros((1, H, W), np.int16)
+        N.check(emu, emu.ovo_sgbm_compute(c.ctx, N.ptr(L), N.ptr(R), W, W * H, 1, N.ptr(out), None))
+        assert np.array_equal(out[0], O.sgbm_compute(L, R, p)), (trial, W, H, D, kw)

@@ -274,3 +274,42 @@ def test_cross_check_opt_in(golden):
     want = [i for i in range(len(fwd)) if float(fwd[i, 1]) < 0.8 * float(fwd[i, 3]) and rev[fwd[i, 0], 0] == i]
     assert od.last_match_count == len(want) < plain.last_match_count
     assert np.array_equal(got, want)
+
+
+def test_sgbm_random_shapes_and_params():
+    # seeded sweep over ragged widths / heights, every block size, padded and unpadded disparity ranges, odd penalties
+    rng = np.random.default_rng(2024)
+    for trial in range(24):
+        D = int(rng.choice([16, 32, 48, 64, 80, 96, 128, 160, 256]))
+        W = D + int(rng.integers(17, 160))
+        H = int(rng.integers(16, 70))
+        bs = int(rng.choice([3, 5, 7, 9, 11]))
+        P1 = int(rng.integers(1, 60)) * bs
+        P2 = P1 + int(rng.integers(1, 400))
+        kw = dict(blockSize=bs, P1=P1, P2=P2, disp12MaxDiff=int(rng.choice([-1, 0, 1, 2, 5])), preFilterCap=int(rng.choice([1, 15, 31, 63])),
+                  uniquenessRatio=int(rng.choice([0, 5, 10, 15, 40])), speckleWindowSize=int(rng.choice([0, 20, 100])),
+                  speckleRange=int(rng.choice([1, 2, 4])))
+        if bs * bs * (2 * (max(kw["preFilterCap"], 15) | 1) + 63) + max(P2, P1 + 1) > 32767:
+            continue
+        cam, args = _cam(W, H, D, **kw)
+        L, R = occluded_pair(W, H, d=min(9, D // 2))
+        got = cam.stereoSGBM.compute(L, R)
+        assert np.array_equal(got, O.sgbm_compute(L, R, args["sgbm_params"])), (trial, W, H, D, kw)
+
+
+def test_orb_random_shapes():
+    # level widths decide where the blur's FMA body ends (w//32*32, w//4*4): sweep ragged sizes, with and without mask
+    rng = np.random.default_rng(77)
+    for trial in range(10):
+        W, H = int(rng.integers(140, 700)), int(rng.integers(130, 400))
+        n = int(rng.choice([50, 300, 1000]))
+        cam, _ = _cam(W, H, 16)
+        od = StereoOdometer(cam, nfeatures=n, preprocessed_frames=True)
+        eng = od._engine()
+        L, _r = synth.kat_pair(W, H, seed=trial)
+        img = np.ascontiguousarray(L[:eng.ch, :eng.cw])
+        mask = block_mask(eng.ch, eng.cw, seed=trial) if trial % 2 else None
+        kps, desc = od.orb.detectAndCompute(img, mask)
+        rk, rd = O.orb_detect_compute(img, mask, n)
+        got = np.array([[k.pt[0], k.pt[1], k.size, k.angle, k.response, k.octave] for k in kps], np.float32).reshape(-1, 6)
+        assert np.array_equal(got, rk) and (len(rk) == 0 or np.array_equal(desc, rd)), (trial, W, H, n)
