@@ -69,7 +69,10 @@ __global__ void k_sgbm_prep(const uint8_t* __restrict__ left, const uint8_t* __r
 // and the vertical window as a ring of horizontal sums in (thread-private, conflict-free) shared memory.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kCostThreads = 128;
-constexpr int kCostRS = 32;
+#ifndef OVO_COST_RS
+#define OVO_COST_RS 32
+#endif
+constexpr int kCostRS = OVO_COST_RS;  // rows per unit (the vertical window adds 2*SW2 halo rows)
 
 __device__ __forceinline__ uint32_t bt_pair(uint32_t lw, uint32_t rw0, uint32_t rw1) {
     // lw: left word at x; rw0 / rw1: right words at x-d and x-d-1
