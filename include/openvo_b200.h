@@ -127,6 +127,14 @@ int ovo_rigid_body_filter(ovo_ctx* ctx, float* pts_prev_dev, float* pts_cur_dev,
 int ovo_outlier_filter(ovo_ctx* ctx, float* pts_prev_dev, float* pts_cur_dev, int32_t* count_dev, int cap, const double* T_dev,
                        double thr, void* stream);
 
+/* §8(f) n4, OPT-IN, not the reference's behaviour (its pose is Umeyama, ovo_rigid_transform): batched P3P RANSAC over a fixed,
+ * seed-determined hypothesis schedule + Levenberg-Marquardt refinement of the reprojection error on the inliers.  3-D points of
+ * frame A (pts1, as produced by ovo_match_points) against the pixel positions of the matched keypoints of frame B (matches[i][1]
+ * indexes kp2).  Intrinsics come from Q (f = Q[2][3], c = -Q[0..1][3]).  iters <= 4096.  Specification: oracle/pnp_restate.py.
+ * out: f64 [16] = rows of [R|t] (12), inlier count, rotation angle, |t|, index of the winning hypothesis. */
+int ovo_pnp_ransac(ovo_ctx* ctx, const float* pts1_dev, const int32_t* matches_dev, const float* kp2_dev, const int32_t* count_dev, int cap,
+                   int iters, double reproj_px, unsigned long long seed, double* out_dev, void* stream);
+
 /* Batched form of S-E + a8/S-F + S-G for n independent frame pairs (n <= max_batch): 2-NN, ratio test + fused 3-D lookup and
  * rigid alignment of every pair in four launches.  `items` is a HOST array; all pointers inside are device pointers.
  * out: f64 [18] per pair = the 16 values of ovo_rigid_transform followed by the two int32 counts of ovo_match_points packed in

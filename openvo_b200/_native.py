@@ -54,6 +54,7 @@ _SIGNATURES = {
     "ovo_knn2_hamming": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),
     "ovo_match_points": (_i, [_vp, _vp, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ovo_rigid_transform": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "ovo_pnp_ransac": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _d, ctypes.c_ulonglong, _vp, _vp]),
     "ovo_rigid_body_filter": (_i, [_vp, _vp, _vp, _vp, _i, _d, _vp]),
     "ovo_outlier_filter": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _d, _vp]),
     "ovo_pair_batch": (_i, [_vp, _i, ctypes.POINTER(PairItem), _d, _vp]),

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libopenvo_b200.so")
-CU = ["api.cu", "sgbm.cu", "orb.cu", "match.cu", "filters.cu"]
+CU = ["api.cu", "sgbm.cu", "orb.cu", "match.cu", "filters.cu", "pnp.cu"]
 CPP = ["host_select.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--fmad=false",
               "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "-Xptxas", "-v"]

@@ -61,6 +61,10 @@ int disp_post_launch(const int16_t* disp, int W, int H, int x0, int y0, int cw, 
 int pair_batch_launch(const GatherParams& gp, int n, const void* items_host, int cap, cudaStream_t st);
 int pair_item_size();
 size_t filter_scratch_bytes(int cap);
+size_t pnp_scratch_bytes(int max_iters, int cap);
+int pnp_ransac_launch(const float* pts, const int32_t* matches, const float* kp2, const int32_t* count, int cap, const double* Q16, int x0,
+                      int y0, int iters, int max_iters, double thr_px, uint64_t seed, uint8_t* scratch, double* out, cudaStream_t st);
+static const int kPnpMaxIters = 4096;
 int rigid_filter_launch(float* prev, float* cur, int32_t* count, int cap, float thr, uint8_t* scratch, cudaStream_t st);
 int outlier_filter_launch(float* prev, float* cur, int32_t* count, int cap, const double* T, double thr, uint8_t* scratch, cudaStream_t st);
 int rectify_launch(const uint8_t* img, int pitch, size_t frame_stride, int ch, int W, int H, int nb, const int16_t* map1,
@@ -73,7 +77,7 @@ struct Layout {
     OrbDims orb;
     int x0, y0, cw, ch;
     size_t sgbm_bytes, orb_bytes, frame_bytes;  // per frame
-    size_t tab_bytes, knn_bytes, nsel_bytes, filter_bytes, total;
+    size_t tab_bytes, knn_bytes, nsel_bytes, filter_bytes, pnp_bytes, total;
     int tab_off[2 * ORB_NLEVELS], tab_total;
 };
 
@@ -117,7 +121,8 @@ static int make_layout(const ovo_config* c, Layout* L) {
     L->knn_bytes = align_up(knn2_scratch_bytes(L->orb.kp_cap, L->orb.kp_cap), 256) * c->max_batch;
     L->nsel_bytes = align_up((size_t)c->max_batch * 4, 256);
     L->filter_bytes = align_up(filter_scratch_bytes(L->orb.kp_cap), 256);
-    L->total = L->frame_bytes * c->max_batch + L->tab_bytes + L->knn_bytes + L->nsel_bytes + L->filter_bytes + 256;
+    L->pnp_bytes = align_up(pnp_scratch_bytes(kPnpMaxIters, L->orb.kp_cap), 256);
+    L->total = L->frame_bytes * c->max_batch + L->tab_bytes + L->knn_bytes + L->nsel_bytes + L->filter_bytes + L->pnp_bytes + 256;
     return 0;
 }
 
@@ -135,6 +140,7 @@ struct ovo_ctx {
     uint32_t* knn_scratch;
     int32_t* nsel_dev;
     uint8_t* filter_scratch;
+    uint8_t* pnp_scratch;
     // pinned host staging for the keypoint selection
     int32_t* h_lvl;    // [max_batch][32]
     float* h_resp;     // [max_batch][cand_cap][2]
@@ -233,7 +239,8 @@ ovo_ctx* ovo_create(const ovo_config* cfg, void* workspace_dev, size_t workspace
     c->tab_dev = (int32_t*)p; p += L.tab_bytes;
     c->knn_scratch = (uint32_t*)p; p += L.knn_bytes;
     c->nsel_dev = (int32_t*)p; p += L.nsel_bytes;
-    c->filter_scratch = p;
+    c->filter_scratch = p; p += L.filter_bytes;
+    c->pnp_scratch = p;
     std::vector<int32_t> tab(L.tab_total);
     int tot;
     orb_make_resize_tables(L.orb, tab.data(), c->L.tab_off, &tot);
@@ -374,6 +381,14 @@ int ovo_pair_batch(ovo_ctx* c, int n, const ovo_pair_item* items, double thr, vo
         if (pair_batch_launch(p, m, tmp.data(), c->L.orb.kp_cap, (cudaStream_t)stream)) return 1;
     }
     return 0;
+}
+
+int ovo_pnp_ransac(ovo_ctx* c, const float* pts1, const int32_t* matches, const float* kp2, const int32_t* count, int cap, int iters,
+                   double reproj_px, unsigned long long seed, double* out, void* stream) {
+    CHECK_CTX(c, 1);
+    if (cap > c->L.orb.kp_cap) { set_error("point capacity exceeds keypoint capacity"); return 1; }
+    return pnp_ransac_launch(pts1, matches, kp2, count, cap, c->cfg.Q, c->L.x0, c->L.y0, iters, kPnpMaxIters, reproj_px, (uint64_t)seed,
+                             c->pnp_scratch, out, (cudaStream_t)stream);
 }
 
 int ovo_rigid_body_filter(ovo_ctx* c, float* pts_prev, float* pts_cur, int32_t* count, int cap, double thr, void* stream) {

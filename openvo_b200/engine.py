@@ -240,6 +240,17 @@ class Engine:
         self._d2h += 128
         return n1, n2, out.cpu().numpy()
 
+    def pnp_ransac(self, b, slot, n, iters, reproj_px, seed):
+        """Opt-in P3P-RANSAC + LM pose (ovo_pnp_ransac) from the buffers the pair step left in `slot`: 3-D points of the query
+        frame and the matched keypoints of frame b.  -> out16 numpy."""
+        cnt = torch.tensor([n], dtype=torch.int32, device=self.device)
+        out = torch.empty(16, dtype=torch.float64, device=self.device)
+        N.check(self.lib, self.lib.ovo_pnp_ransac(self.ctx, self.pts1[slot].data_ptr(), self.matches[slot].data_ptr(), b.kp.data_ptr(),
+                                                  cnt.data_ptr(), self.kp_cap, int(iters), float(reproj_px), int(seed), out.data_ptr(),
+                                                  self._stream()))
+        self._d2h += 128
+        return out.cpu().numpy()
+
     def rigid(self, pts1, pts2):
         """numpy float32 [m,3] x2 -> out16 (estimateAffine3D seam for the optional filter paths)."""
         m = len(pts1)

@@ -78,7 +78,8 @@ class StereoOdometer:
     MAX_ROTATION_CHANGE = np.pi / 3
 
     def __init__(self, stereo_camera, nfeatures=500, match_threshold=0.8, rigidity_threshold=0, outlier_threshold=0,
-                 preprocessed_frames=False, min_matches=10, cross_check=False, _max_batch=1, _engine_tag=0):
+                 preprocessed_frames=False, min_matches=10, cross_check=False, pose_method="umeyama", ransac_iters=512,
+                 ransac_reproj_px=8.0, ransac_seed=0, _max_batch=1, _engine_tag=0):
         self.stereo = stereo_camera
         self._nfeatures = nfeatures
         self._max_batch = _max_batch  # >1 only when driven by openvo_b200.batch.BatchOdometer
@@ -91,6 +92,11 @@ class StereoOdometer:
         self.min_matches = min_matches
         # opt-in extension: left-right cross-check of the matches (the reference's "TODO crosscheck", stereo_odometer.py:21)
         self.cross_check = cross_check
+        # opt-in extension (north-star stage 5): "pnp_ransac" = batched P3P RANSAC + LM instead of the reference's Umeyama alignment
+        if pose_method not in ("umeyama", "pnp_ransac"):
+            raise ValueError("pose_method must be 'umeyama' (the reference's behaviour) or 'pnp_ransac'")
+        self.pose_method, self.ransac_iters = pose_method, ransac_iters
+        self.ransac_reproj_px, self.ransac_seed = ransac_reproj_px, ransac_seed
         self.skipped_frames = 0
         self.c_T_w = np.eye(4)
         self.c_T_w_prev = np.eye(4)
@@ -226,6 +232,11 @@ class StereoOdometer:
             return self._filtered(eng.pts1[slot], eng.pts2[slot], cnt)
         if n < 10:
             self.skip_cause = "rigidity"
+        if self.pose_method == "pnp_ransac":
+            out = eng.pnp_ransac(b, slot, n, self.ransac_iters, self.ransac_reproj_px, self.ransac_seed)
+            if not (out[12] >= self.min_matches):   # too few inliers (or no valid hypothesis)
+                self.skip_cause = "ransac"
+                return None
         return self._gate(out)
 
     def _gate(self, out):

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.abspath(os.path.join(HERE, "..", ".."))
 CSRC = os.path.join(ROOT, "openvo_b200", "csrc")
 OUT = os.path.join(HERE, "_build", "libopenvo_b200_emu.so")
-SRCS = ["api.cu", "sgbm.cu", "orb.cu", "match.cu", "filters.cu", "host_select.cpp"]
+SRCS = ["api.cu", "sgbm.cu", "orb.cu", "match.cu", "filters.cu", "pnp.cu", "host_select.cpp"]
 
 
 def build(force=False):

@@ -61,6 +61,7 @@ enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 #define __align__(n) __attribute__((aligned(n)))
 using std::isinf;
 using std::isnan;
+using std::isfinite;
 
 // ---- execution engine ---------------------------------------------------------------------------------------
 namespace ovo_emu {

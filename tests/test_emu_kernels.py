@@ -274,3 +274,50 @@ def test_sgbm_kernels_random_small(emu):
         out = np.zeros((1, H, W), np.int16)
         N.check(emu, emu.ovo_sgbm_compute(c.ctx, N.ptr(L), N.ptr(R), W, W * H, 1, N.ptr(out), None))
         assert np.array_equal(out[0], O.sgbm_compute(L, R, p)), (trial, W, H, D, kw)
+
+
+def _pnp_case(seed=0, m=500, n_out=120):
+    from oracle import pnp_restate as P
+    rng = np.random.default_rng(seed)
+    f, cx, cy = 300.0, 149.5, 74.5
+    X = np.stack([rng.uniform(-8, 8, m), rng.uniform(-2, 2, m), rng.uniform(5, 25, m)], 1).astype(np.float32)
+    R = P.rodrigues(np.array([0.01, -0.03, 0.005]))
+    t = np.array([0.03, -0.01, -0.2])
+    uv, _ = P.project(R, t, X.astype(np.float64), f, cx, cy)
+    uv += rng.normal(0, 0.3, uv.shape)
+    out = rng.choice(m, n_out, replace=False)
+    uv[out] += rng.normal(0, 40, (n_out, 2))
+    kp2 = np.zeros((m, 6), np.float32)
+    kp2[:, :2] = uv
+    matches = np.stack([np.arange(m), rng.permutation(m), np.zeros(m)], 1).astype(np.int32)
+    kp2p = np.zeros_like(kp2)
+    kp2p[matches[:, 1]] = kp2           # keypoint of match i sits at row matches[i][1]
+    Q = np.array([[1, 0, 0, -cx], [0, 1, 0, -cy], [0, 0, 0, f], [0, 0, 1 / 0.537, 0.0]])
+    return X, kp2p, matches, Q, (f, cx, cy), (R, t)
+
+
+def test_pnp_ransac_kernels(emu):
+    """opt-in P3P-RANSAC + LM vs its numpy specification: same winning hypothesis, same inlier count,
+    pose within the north-star tolerance (1e-4 rad, 1e-3 relative translation)."""
+    from oracle import pnp_restate as P
+    X, kp2, matches, Q, (f, cx, cy), _ = _pnp_case()
+    W, H = 300, 150
+    c = Ctx(emu, W, H, sgbm_params(32), (0, 0, W, H), Q, 600)
+    m = len(X)
+    pts = np.zeros((c.cap, 3), np.float32)
+    pts[:m] = X
+    mt = np.zeros((c.cap, 3), np.int32)
+    mt[:m] = matches
+    kp = np.zeros((c.cap, 6), np.float32)
+    kp[:m] = kp2
+    cnt = np.array([m], np.int32)
+    out = np.zeros(16)
+    iters, seed = 64, 3
+    N.check(emu, emu.ovo_pnp_ransac(c.ctx, N.ptr(pts), N.ptr(mt), N.ptr(kp), N.ptr(cnt), c.cap, iters, 8.0, seed, N.ptr(out), None))
+    uv = kp2[matches[:, 1], :2].astype(np.float64)
+    ref = P.pnp_ransac(X.astype(np.float64), uv, f, cx, cy, iters=iters, thr=8.0, seed=seed)
+    assert int(out[15]) == ref["best"] and int(out[12]) == ref["n_inliers"] > 300
+    Rg, tg = out[:12].reshape(3, 4)[:, :3], out[:12].reshape(3, 4)[:, 3]
+    dR = Rg @ ref["R"].T
+    assert np.arccos(np.clip((np.trace(dR) - 1) / 2, -1, 1)) < 1e-4
+    assert np.linalg.norm(tg - ref["t"]) < 1e-3 * np.linalg.norm(ref["t"])

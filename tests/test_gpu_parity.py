@@ -313,3 +313,43 @@ def test_orb_random_shapes():
         rk, rd = O.orb_detect_compute(img, mask, n)
         got = np.array([[k.pt[0], k.pt[1], k.size, k.angle, k.response, k.octave] for k in kps], np.float32).reshape(-1, 6)
         assert np.array_equal(got, rk) and (len(rk) == 0 or np.array_equal(desc, rd)), (trial, W, H, n)
+
+
+def test_pnp_ransac_opt_in(golden):
+    # extension row n4: batched P3P RANSAC + LM vs its numpy specification (oracle/pnp_restate.py), then through the odometer
+    import ctypes
+    import torch
+    from oracle import pnp_restate as P
+    from openvo_b200 import _native as N
+    from test_emu_kernels import _pnp_case
+    X, kp2, matches, Q, (f, cx, cy), _ = _pnp_case(seed=1, m=1500, n_out=400)
+    cam, _ = _cam(300, 150, 32)
+    eng = cam.engine(nfeatures=2000)
+    eng.cfg.Q[:] = (ctypes.c_double * 16)(*Q.reshape(-1))      # synthetic intrinsics for this unit test
+    ctx2 = eng.lib.ovo_create(ctypes.byref(eng.cfg), eng.workspace.data_ptr(), eng.workspace.numel())
+    m = len(X)
+    pts = torch.zeros((eng.kp_cap, 3), dtype=torch.float32, device="cuda"); pts[:m] = torch.from_numpy(X).cuda()
+    mt = torch.zeros((eng.kp_cap, 3), dtype=torch.int32, device="cuda"); mt[:m] = torch.from_numpy(matches).cuda()
+    kp = torch.zeros((eng.kp_cap, 6), dtype=torch.float32, device="cuda"); kp[:m] = torch.from_numpy(kp2).cuda()
+    cnt = torch.tensor([m], dtype=torch.int32, device="cuda")
+    out = torch.zeros(16, dtype=torch.float64, device="cuda")
+    N.check(eng.lib, eng.lib.ovo_pnp_ransac(ctx2, pts.data_ptr(), mt.data_ptr(), kp.data_ptr(), cnt.data_ptr(), eng.kp_cap, 1024, 8.0, 7,
+                                            out.data_ptr(), None))
+    o = out.cpu().numpy()
+    eng.lib.ovo_destroy(ctx2)
+    ref = P.pnp_ransac(X.astype(np.float64), kp2[matches[:, 1], :2].astype(np.float64), f, cx, cy, iters=1024, thr=8.0, seed=7)
+    assert int(o[15]) == ref["best"] and int(o[12]) == ref["n_inliers"] > 900
+    T, Tr = np.eye(4), np.eye(4)
+    T[:3, :4] = o[:12].reshape(3, 4)
+    Tr[:3, :3], Tr[:3, 3] = ref["R"], ref["t"]
+    assert _pose_close(T, Tr)
+    # through the odometer: same frames, opt-in estimator; commits frames and lands near the reference's Umeyama pose
+    g = golden("seq_small")
+    W, H, D, n = int(g["W"]), int(g["H"]), int(g["D"]), int(g["nfeatures"])
+    cam2, _ = _cam(W, H, D)
+    od = StereoOdometer(cam2, nfeatures=n, preprocessed_frames=True, pose_method="pnp_ransac", ransac_iters=512, ransac_seed=1)
+    od2 = StereoOdometer(cam2, nfeatures=n, preprocessed_frames=True, pose_method="pnp_ransac", ransac_iters=512, ransac_seed=1)
+    for i in range(3):
+        assert od.update(g["left"][i], g["right"][i]) and od2.update(g["left"][i], g["right"][i])
+    assert np.array_equal(od.c_T_w, od2.c_T_w)                      # deterministic for a fixed seed and schedule
+    assert np.linalg.norm(od.c_T_w[:3, 3] - g["cTw_2"][:3, 3]) < 0.5

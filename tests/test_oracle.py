@@ -183,3 +183,29 @@ def test_sgbm_mode_hh_restated_equals_cv2():
         p = sgbm_params(D, **kw)
         ref = cv2.StereoSGBM_create(*[p[k] for k in O.SGBM_KEYS], mode=cv2.STEREO_SGBM_MODE_HH).compute(L, R)
         assert np.array_equal(O.sgbm_compute_mode(L, R, p, 1), ref)
+
+
+def test_pnp_ransac_specification_vs_cv2_and_truth():
+    # extension row n4 (parity unpinned: OpenCV's RNG schedule is not reproducible): the numpy specification recovers the pose
+    # and coincides with cv2.solvePnPRansac whenever the inlier sets coincide
+    from oracle import pnp_restate as P
+    rng = np.random.default_rng(0)
+    f, cx, cy = 718.856, 620.0, 187.5
+    m = 600
+    X = np.stack([rng.uniform(-8, 8, m), rng.uniform(-2, 2, m), rng.uniform(5, 25, m)], 1)
+    R, t = P.rodrigues(np.array([0.01, -0.03, 0.005])), np.array([0.03, -0.01, -0.2])
+    uv, _ = P.project(R, t, X, f, cx, cy)
+    # exact P3P on three clean correspondences
+    bear = np.stack([(uv[:3, 0] - cx) / f, (uv[:3, 1] - cy) / f, np.ones(3)], 1)
+    bear /= np.linalg.norm(bear, axis=1, keepdims=True)
+    sols = P.p3p(X[:3], bear)
+    assert min(np.abs(s[0] - R).max() + np.abs(s[1] - t).max() for s in sols) < 1e-9
+    uv = uv + rng.normal(0, 0.3, uv.shape)
+    out = rng.choice(m, 150, replace=False)
+    uv[out] += rng.normal(0, 40, (150, 2))
+    r = P.pnp_ransac(X, uv, f, cx, cy, iters=256, thr=8.0, seed=3)
+    dR = r["R"] @ R.T
+    assert np.arccos(np.clip((np.trace(dR) - 1) / 2, -1, 1)) < 2e-4 and np.linalg.norm(r["t"] - t) < 2e-3
+    ok, rv, tv, inl = cv2.solvePnPRansac(X, uv, np.array([[f, 0, cx], [0, f, cy], [0, 0, 1]]), None, iterationsCount=256, reprojectionError=8.0)
+    if ok and len(inl) == r["n_inliers"]:
+        assert np.abs(cv2.Rodrigues(rv)[0] - r["R"]).max() < 1e-6 and np.abs(tv.ravel() - r["t"]).max() < 1e-6
