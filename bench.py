@@ -104,9 +104,10 @@ def run_cpu(cfg_key, L, R, warmup, steps, nprocs):
 
 def host_cores():
     try:
-        return len(os.sched_getaffinity(0))
+        n = len(os.sched_getaffinity(0))
     except Exception:
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    return max(1, min(n, 128))  # one single-threaded reference process per core; capped to bound memory on very wide hosts
 
 
 # ---------------------------------------------------------------------------------------------------------------------------
