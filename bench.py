@@ -238,6 +238,8 @@ def main():
         return [BatchOdometer(cam, SP, nfeatures=cfg["n"], engine_tag=t, preprocessed_frames=True) for t in range(NT)]
 
     dev_L, dev_R = torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()
+    pin_L = [torch.from_numpy(L[i]).pin_memory() for i in range(len(L))]   # e2e inputs: host frames in pinned memory
+    pin_R = [torch.from_numpy(R[i]).pin_memory() for i in range(len(R))]
     lib = _native.load()
 
     def run_part(bo, t, steps, first_step, host):
@@ -245,7 +247,7 @@ def main():
         for s in range(first_step, first_step + steps):
             idx = [frame_index(s, rank * S + t * SP + q) for q in range(SP)]
             if host:
-                res = bo.update([L[i] for i in idx], [R[i] for i in idx])  # one host array per sequence, as a loader would hand them over
+                res = bo.update([pin_L[i] for i in idx], [pin_R[i] for i in idx])  # one pinned host frame per sequence, H2D every step
             else:
                 ti = torch.tensor(idx, device="cuda")
                 res = bo.update_device(dev_L[ti], dev_R[ti])

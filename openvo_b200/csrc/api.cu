@@ -1,6 +1,7 @@
 // C ABI of openvo_b200 (include/openvo_b200.h): context, workspace carving and the per-seam entry points.
 #include <atomic>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -326,10 +327,16 @@ int ovo_orb_detect_compute(ovo_ctx* c, const uint8_t* img, const uint8_t* mask, 
     auto select_one = [&](int f) {
         c->h_nsel[f] = orb_host_select(d, c->h_lvl + 32 * f, c->h_resp + (size_t)f * d.cand_cap * 2, c->h_sel + (size_t)f * d.kp_cap);
     };
-    if (nb == 1) select_one(0);
-    else {
+    static const int max_threads = [] {
+        const char* e = getenv("OVO_SELECT_THREADS");   // host threads used for the per-frame retainBest emulation (default 4)
+        const int v = e ? atoi(e) : 4;
+        return v < 1 ? 1 : (v > 16 ? 16 : v);
+    }();
+    if (nb == 1 || max_threads == 1) {
+        for (int f = 0; f < nb; f++) select_one(f);
+    } else {
         std::vector<std::thread> th;
-        const int nth = nb < 16 ? nb : 16;
+        const int nth = nb < max_threads ? nb : max_threads;
         for (int t = 0; t < nth; t++)
             th.emplace_back([&, t] { for (int f = t; f < nb; f += nth) select_one(f); });
         for (auto& x : th) x.join();

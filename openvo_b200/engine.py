@@ -90,6 +90,13 @@ class Engine:
 
     def upload(self, arr, key):
         """numpy uint8 [nb,H,W(,3)] (or a list of nb frames) -> device tensor via a pinned staging buffer (one host copy)."""
+        if isinstance(arr, (list, tuple)) and isinstance(arr[0], torch.Tensor):
+            # frames that already live in pinned host memory (a loader decoding into pinned buffers): straight H2D, no staging copy
+            dst = torch.empty((len(arr),) + tuple(arr[0].shape), dtype=torch.uint8, device=self.device)
+            for i, fr in enumerate(arr):
+                dst[i].copy_(fr, non_blocking=True)
+                self._h2d += fr.numel()
+            return dst
         if isinstance(arr, (list, tuple)):
             first = np.asarray(arr[0])
             stage = self._pinned(key, (len(arr),) + first.shape, torch.uint8)

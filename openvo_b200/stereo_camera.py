@@ -111,9 +111,15 @@ class StereoCamera:
         return img[r[1]:r[3], r[0]:r[2]]
 
     def _check(self, img):
-        if img.dtype != np.uint8 or img.ndim not in (2, 3) or (img.ndim == 3 and img.shape[2] != 3):
+        if hasattr(img, "data_ptr"):  # torch CPU tensor
+            import torch
+            if img.dtype != torch.uint8 or img.device.type != "cpu" or not img.is_contiguous():
+                raise ValueError("torch frames must be contiguous uint8 CPU (ideally pinned) tensors")
+        elif img.dtype != np.uint8:
+            raise ValueError("images must be uint8 (the reference raises cv2.error here)")
+        if len(img.shape) not in (2, 3) or (len(img.shape) == 3 and img.shape[2] != 3):
             raise ValueError("images must be uint8, HxW (gray) or HxWx3 (BGR) (the reference raises cv2.error here)")
-        if img.shape[:2] != (self.img_size[1], self.img_size[0]):
+        if tuple(img.shape[:2]) != (self.img_size[1], self.img_size[0]):
             raise ValueError("image size differs from the camera's img_size")
 
     def _prepare_device(self, eng, img_left, img_right, preprocessed, key="prep"):
@@ -122,10 +128,10 @@ class StereoCamera:
         out = []
         for side, img in (("left", img_left), ("right", img_right)):
             hw = (self.img_size[1], self.img_size[0])
-            if isinstance(img, (list, tuple)):   # one array per sequence: copied straight into the pinned staging buffer
+            if isinstance(img, (list, tuple)):   # one array (or pinned torch tensor) per sequence
                 for fr in img:
-                    self._check(np.asarray(fr))
-                colour = np.asarray(img[0]).ndim == 3
+                    self._check(fr if hasattr(fr, "data_ptr") else np.asarray(fr))
+                colour = len(img[0].shape) == 3
             else:
                 img = np.asarray(img)
                 if img.shape[:2] == hw and img.ndim in (2, 3):  # a single frame
