@@ -356,3 +356,18 @@ def test_pnp_ransac_opt_in(golden):
     _, _, poses = synth.make_sequence(W, H, 3)
     assert np.linalg.norm(od.c_T_w[:3, 3] - poses[2][:3, 3]) < 0.03
     assert np.linalg.norm(g["cTw_2"][:3, 3] - poses[2][:3, 3]) > np.linalg.norm(od.c_T_w[:3, 3] - poses[2][:3, 3])
+
+
+def test_update_vs_oracle_1080p_shape():
+    # BASELINE config 3: 1920x1080, ORB 5000, 256 disparities — whole update() against the cv2-backed port
+    W, H, D, n = 1920, 1080, 256, 5000
+    Ls, Rs, _ = synth.make_sequence(W, H, 2)
+    cam, args = _cam(W, H, D)
+    od = StereoOdometer(cam, nfeatures=n, preprocessed_frames=True)
+    po = O.StereoOdometerPort(O.StereoCameraPort(**args, backend="cv2"), nfeatures=n, preprocessed_frames=True)
+    for i in range(2):
+        assert od.update(Ls[i], Rs[i]) == po.update(Ls[i], Rs[i])
+        assert np.array_equal(od.current_disparity, po.cur[1])
+        assert np.array_equal(od._host(od._cur, "kp_array"), po.cur[3]) and np.array_equal(od.current_desc, po.cur[4])
+    assert np.array_equal(od._engine().matches[0, :od.last_match_count].cpu().numpy(), po.last_matches)
+    assert od.skip_cause == po.skip_cause and _pose_close(od.c_T_w, po.c_T_w)
