@@ -371,3 +371,25 @@ def test_update_vs_oracle_1080p_shape():
         assert np.array_equal(od._host(od._cur, "kp_array"), po.cur[3]) and np.array_equal(od.current_desc, po.cur[4])
     assert np.array_equal(od._engine().matches[0, :od.last_match_count].cpu().numpy(), po.last_matches)
     assert od.skip_cause == po.skip_cause and _pose_close(od.c_T_w, po.c_T_w)
+
+
+def test_reference_error_behaviour():
+    """The reference's hard failures are reproduced, not swallowed: all four taps of a lookup unusable -> ZeroDivisionError
+    (ref: src/openVO/stereo_odometer.py:79 with num = den = 0); a next frame with a single keypoint -> IndexError (ref: :164)."""
+    import torch
+    from openvo_b200.engine import Frame
+    W, H, D, n = 480, 160, 64, 400
+    Ls, Rs, _ = synth.make_sequence(W, H, 2)
+    cam, _ = _cam(W, H, D)
+    od = StereoOdometer(cam, nfeatures=n, preprocessed_frames=True)
+    assert od.update(Ls[0], Rs[0])
+    eng = od._engine()
+    good = od._cur
+    # same features, but a disparity map that is 0 everywhere: reprojection gives +-inf at every tap
+    zero = Frame(good.img, torch.zeros_like(good.disp), good.kp, good.desc, good.n_kp)
+    with pytest.raises(ZeroDivisionError):
+        od._relative(zero, zero)
+    one = Frame(good.img, good.disp, good.kp, good.desc, 1)
+    od.min_matches = 1
+    with pytest.raises(IndexError):
+        od._relative(good, one)
