@@ -46,6 +46,9 @@ class Ctx:
     (200, 36, 64, 1, dict(blockSize=3, P1=72, P2=288, uniquenessRatio=0, speckleWindowSize=0)),
     (150, 40, 48, 1, dict(blockSize=7, preFilterCap=15, uniquenessRatio=15, disp12MaxDiff=2, speckleWindowSize=50, speckleRange=1)),
     (200, 34, 128, 2, {}),
+    (190, 21, 128, 1, dict(uniquenessRatio=0)),                                  # odd height: the two-rows-per-warp kernel's tail
+    (170, 19, 96, 1, dict(blockSize=3, P1=72, P2=288, disp12MaxDiff=2)),        # padded 96 -> 128
+    (180, 18, 112, 1, dict(mode=1)),                                            # opt-in MODE_HH through the same kernel
 ])
 def test_sgbm_kernels(emu, W, H, D, nb, kw):
     p = sgbm_params(D, **kw)
@@ -56,7 +59,7 @@ def test_sgbm_kernels(emu, W, H, D, nb, kw):
     out = np.zeros((nb, H, W), np.int16)
     N.check(emu, emu.ovo_sgbm_compute(c.ctx, N.ptr(Ls), N.ptr(Rs), W, W * H, nb, N.ptr(out), None))
     for f in range(nb):
-        assert np.array_equal(out[f], O.sgbm_compute(Ls[f], Rs[f], p))
+        assert np.array_equal(out[f], O.sgbm_compute_mode(Ls[f], Rs[f], p, p.get("mode", 0)))
 
 
 @pytest.mark.parametrize("W,H,n,usemask,nb", [(320, 120, 300, False, 1), (300, 170, 300, True, 2)])
