@@ -575,272 +575,6 @@ __global__ void __launch_bounds__(64, OVO_HOR_MINB) k_sgbm_horiz(SgbmDims d, Sgb
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Same kernel for a 128-wide (padded) disparity range with HALF a warp per cost vector: 16 lanes x 4 packed registers,
-// so one warp carries two image rows.  The per-step overhead (pointer stepping, prefetch bookkeeping, loop control) and the
-// shuffles are shared by two cells and the two rows give every warp two independent dependency chains; per-half minima are
-// 4-stage shuffle butterflies instead of CREDUX.
-// ------------------------------------------------------------------------------------------------------------
-template <bool PAD>
-__device__ __forceinline__ void path_step16(uint32_t (&L)[4], uint32_t& m, const uint32_t (&c)[4], const uint32_t (&padmask)[4],
-                                            uint32_t P1P1, uint32_t P2, bool sub_first, bool sub_last) {
-    uint32_t below = __shfl_up_sync(0xffffffffu, L[3], 1, 16);
-    uint32_t above = __shfl_down_sync(0xffffffffu, L[0], 1, 16);
-    if (sub_first) below = kMaxC2;
-    if (sub_last) above = kMaxC2;
-    const uint32_t mP2 = bcast16(m + P2), mm = bcast16(m);
-    uint32_t out[4];
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-        const uint32_t dm1 = __funnelshift_l(r == 0 ? below : L[r - 1], L[r], 16);
-        const uint32_t dp1 = __funnelshift_r(L[r], r == 3 ? above : L[r + 1], 16);
-        uint32_t t = __viaddmin_u16x2(dm1, P1P1, L[r]);
-        t = __viaddmin_u16x2(dp1, P1P1, t);
-        t = __vminu2(t, mP2);
-        out[r] = c[r] + (t - mm);
-        if (PAD) out[r] |= padmask[r];
-    }
-    uint32_t t = __vminu2(__vminu2(out[0], out[1]), __vminu2(out[2], out[3]));
-#pragma unroll
-    for (int r = 0; r < 4; r++) L[r] = out[r];
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) t = __vminu2(t, __shfl_xor_sync(0xffffffffu, t, o, 16));
-    m = min(t & 0xFFFFu, t >> 16);
-}
-
-template <bool PAD>
-__device__ __forceinline__ void wta_cell16(const uint32_t (&S)[4], int sub, const SgbmDims& d, int x1, bool row_ok, uint32_t* selA,
-                                           uint32_t* selB, uint16_t* selBest) {
-    const int D = d.D;
-    const int dd0 = 8 * sub;
-    uint32_t kbest = 0xFFFFFFFFu;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        const uint32_t key = half_of<4>(S, k) * 512u + (uint32_t)(dd0 + k);
-        if (!PAD || dd0 + k < D) kbest = min(kbest, key);
-    }
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) kbest = min(kbest, __shfl_xor_sync(0xffffffffu, kbest, o, 16));
-    const int minS = (int)(kbest >> 9), best = (int)(kbest & 511u);
-    const int fac = 100 - d.uniq;
-    uint32_t m2 = 0xFFFFu;
-    if (fac > 0) {
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const bool far = (uint32_t)(dd0 + k - best + 1) > 2u && (!PAD || dd0 + k < D);
-            m2 = min(m2, far ? half_of<4>(S, k) : 0xFFFFu);
-        }
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) m2 = min(m2, __shfl_xor_sync(0xffffffffu, m2, o, 16));
-    } else {
-        uint32_t bad = 0;
-#pragma unroll
-        for (int k = 0; k < 8; k++)
-            if ((!PAD || dd0 + k < D) && (int)half_of<4>(S, k) * fac < minS * 100 && abs(dd0 + k - best) > 1) bad = 1;
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) bad |= __shfl_xor_sync(0xffffffffu, bad, o, 16);
-        m2 = bad ? 0u : 0xFFFFu;
-    }
-    auto at = [&](int dd) -> uint32_t {  // S[dd], dd uniform within the half warp
-        const int r = (dd & 7) >> 1;
-        uint32_t w = S[0];
-        if (r == 1) w = S[1];
-        if (r == 2) w = S[2];
-        if (r == 3) w = S[3];
-        w = __shfl_sync(0xffffffffu, w, dd >> 3, 16);
-        return (dd & 1) ? (w >> 16) : (w & 0xFFFFu);
-    };
-    const uint32_t sm1 = at(max(best - 1, 0)), sp1 = at(min(best + 1, D - 1));
-    if (sub == 0 && row_ok) {
-        selA[x1] = (uint32_t)minS | (m2 << 16);
-        selB[x1] = sm1 | (sp1 << 16);
-        selBest[x1] = (uint16_t)best;
-    }
-}
-
-template <bool PAD>
-__global__ void __launch_bounds__(64) k_sgbm_horiz2(SgbmDims d, SgbmWorkspace ws, size_t ws_stride) {
-    OVO_DYN_SMEM(uint32_t, hsm);
-    constexpr int NPR = 4, WPC = 64, PF1 = 2, PF2 = 3;
-    const int W = d.W, W1 = d.W1, H = d.H;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, sub = lane & 15, hrow = lane >> 4;
-    const int f = blockIdx.y;
-    const int y = 2 * blockIdx.x + hrow;
-    const bool row_ok = y < H;
-    const int yc = row_ok ? y : H - 1;
-    const int row_words = (6 * W + 10 * W1 + 15) / 16 * 4;  // per-row shared arrays, 16-byte granules
-    auto arrays = [&](int r, uint32_t*& d2key, uint32_t*& selA, uint32_t*& selB, int16_t*& disp1s, uint16_t*& selBest) {
-        d2key = hsm + (size_t)r * row_words;
-        selA = d2key + W;
-        selB = selA + W1;
-        disp1s = reinterpret_cast<int16_t*>(selB + W1);
-        selBest = reinterpret_cast<uint16_t*>(disp1s + W);
-    };
-    uint32_t *d2key, *selA, *selB;
-    int16_t* disp1s;
-    uint16_t* selBest;
-    for (int r = 0; r < 2; r++) {
-        arrays(r, d2key, selA, selB, disp1s, selBest);
-        for (int i = threadIdx.x; i < W; i += blockDim.x) {
-            d2key[i] = kD2Init;
-            disp1s[i] = (int16_t)kInv;
-        }
-    }
-    __syncthreads();
-    arrays(hrow, d2key, selA, selB, disp1s, selBest);
-
-    const size_t rowoff = (size_t)yc * W1 * WPC + sub * NPR;
-    const size_t vol = (size_t)H * W1 * WPC;
-    const uint32_t* C = reinterpret_cast<const uint32_t*>(frame_ptr(ws.C, ws_stride, f)) + rowoff;
-    const uint32_t* L1 = reinterpret_cast<const uint32_t*>(frame_ptr(ws.Lv, ws_stride, f)) + rowoff;
-    uint32_t* T = const_cast<uint32_t*>(L1) + vol;
-    const uint32_t* L3 = L1 + 2 * vol;
-
-    uint32_t padmask[NPR];
-#pragma unroll
-    for (int r = 0; r < NPR; r++) padmask[r] = (2 * (NPR * sub + r) >= d.D) ? kMaxC2 : 0u;
-    const uint32_t P1P1 = bcast16(d.P1), P2 = d.P2;
-    const bool sub_first = sub == 0, sub_last = sub == 15;
-    const int mid = W1 >> 1;
-    const int dirx = wid == 0 ? 1 : -1;
-    const int xa = wid == 0 ? 0 : W1 - 1;
-    const int n1 = wid == 0 ? mid : W1 - mid;
-    const int n2 = W1 - n1;
-    const ptrdiff_t dstep = dirx * WPC;
-    const bool hh = d.mode != 0;
-
-    uint32_t L[NPR] = {0, 0, 0, 0}, m = 0;
-    {   // ---- phase 1: T = sat(L1 + L2 + L3 (+ the bottom-up three in MODE_HH) + own)
-        uint32_t cb[PF1][NPR], l1[PF1][NPR], l2[PF1][NPR], l3[PF1][NPR];
-        const uint32_t *pc = C + xa * WPC, *p1 = L1 + xa * WPC, *p3 = L3 + xa * WPC, *p2 = T + xa * WPC, *pu = L1 + 3 * vol + xa * WPC;
-        uint32_t* po = T + xa * WPC;
-#pragma unroll
-        for (int i = 0; i < PF1; i++) {
-            if (i < n1) { ldv<NPR>(cb[i], pc); ldv<NPR>(l1[i], p1); ldv<NPR>(l2[i], p2); ldv<NPR>(l3[i], p3); }
-            pc += dstep; p1 += dstep; p2 += dstep; p3 += dstep;
-        }
-        auto body = [&](int i, bool pf) {
-            uint32_t c[NPR], sv[NPR];
-#pragma unroll
-            for (int r = 0; r < NPR; r++) {
-                c[r] = cb[i][r];
-                sv[r] = __viaddmin_u16x2(__viaddmin_u16x2(l1[i][r], l2[i][r], kMaxC2), l3[i][r], kMaxC2);
-            }
-            if (hh) {
-#pragma unroll
-                for (int v = 0; v < 3; v++) {
-                    uint32_t u[NPR];
-                    ldv<NPR>(u, pu + (size_t)v * vol);
-#pragma unroll
-                    for (int r = 0; r < NPR; r++) sv[r] = __viaddmin_u16x2(sv[r], u[r], kMaxC2);
-                }
-                pu += dstep;
-            }
-            if (pf) { ldv<NPR>(cb[i], pc); ldv<NPR>(l1[i], p1); ldv<NPR>(l2[i], p2); ldv<NPR>(l3[i], p3); }
-            pc += dstep; p1 += dstep; p2 += dstep; p3 += dstep;
-            path_step16<PAD>(L, m, c, padmask, P1P1, P2, sub_first, sub_last);
-#pragma unroll
-            for (int r = 0; r < NPR; r++) sv[r] = __viaddmin_u16x2(sv[r], L[r], kMaxC2);
-            if (row_ok) stv<NPR>(po, sv);
-            po += dstep;
-        };
-        int k = 0;
-        for (; k + 2 * PF1 <= n1; k += PF1) {
-#pragma unroll
-            for (int i = 0; i < PF1; i++) body(i, true);
-        }
-        for (; k < n1; k += PF1) {
-#pragma unroll
-            for (int i = 0; i < PF1; i++)
-                if (k + i < n1) body(i, k + i + PF1 < n1);
-        }
-    }
-    __syncthreads();
-    {   // ---- phase 2: S = sat(T_other + own) -> selection
-        const int xb = xa + dirx * n1;
-        uint32_t cb[PF2][NPR], tb[PF2][NPR];
-        const uint32_t *pc = C + xb * WPC, *pt = T + xb * WPC;
-#pragma unroll
-        for (int i = 0; i < PF2; i++) {
-            if (i < n2) { ldv<NPR>(cb[i], pc); ldv<NPR>(tb[i], pt); }
-            pc += dstep; pt += dstep;
-        }
-        int x1 = xb;
-        if (n1 == 0) {
-#pragma unroll
-            for (int r = 0; r < NPR; r++) L[r] = 0;
-            m = 0;
-        }
-        auto body = [&](int i, bool pf) {
-            uint32_t c[NPR], S[NPR];
-#pragma unroll
-            for (int r = 0; r < NPR; r++) { c[r] = cb[i][r]; S[r] = tb[i][r]; }
-            if (pf) { ldv<NPR>(cb[i], pc); ldv<NPR>(tb[i], pt); }
-            pc += dstep; pt += dstep;
-            path_step16<PAD>(L, m, c, padmask, P1P1, P2, sub_first, sub_last);
-#pragma unroll
-            for (int r = 0; r < NPR; r++) S[r] = __viaddmin_u16x2(S[r], L[r], kMaxC2);
-            wta_cell16<PAD>(S, sub, d, x1, row_ok, selA, selB, selBest);
-            x1 += dirx;
-        };
-        int k = 0;
-        for (; k + 2 * PF2 <= n2; k += PF2) {
-#pragma unroll
-            for (int i = 0; i < PF2; i++) body(i, true);
-        }
-        for (; k < n2; k += PF2) {
-#pragma unroll
-            for (int i = 0; i < PF2; i++)
-                if (k + i < n2) body(i, k + i + PF2 < n2);
-        }
-    }
-    __syncthreads();
-    // ---- uniqueness, sub-pixel refinement, disp2 (A.4.4) and LR check (A.4.5), data-parallel over both rows
-    const int D = d.D, fac = 100 - d.uniq;
-    for (int r = 0; r < 2; r++) {
-        if (2 * (int)blockIdx.x + r >= H) break;
-        arrays(r, d2key, selA, selB, disp1s, selBest);
-        for (int x1 = threadIdx.x; x1 < W1; x1 += blockDim.x) {
-            const uint32_t a = selA[x1], b = selB[x1];
-            const int minS = (int)(a & 0xFFFFu), m2 = (int)(a >> 16), best = selBest[x1];
-            const bool reject = fac > 0 ? (m2 * fac < minS * 100) : (m2 == 0);
-            if (reject) continue;
-            const int x = x1 + D;
-            if (minS < 32767) atomicMin(&d2key[x - best], ((uint32_t)minS << 16) | (uint32_t)(0xFFFF - best));
-            int dsp = best * 16;
-            if (best > 0 && best < D - 1) {
-                const int sm1 = (int)(b & 0xFFFFu), sp1 = (int)(b >> 16);
-                const int den = max(sm1 + sp1 - 2 * minS, 1);
-                dsp += ((sm1 - sp1) * 16 + den) / (2 * den);
-            }
-            disp1s[x] = (int16_t)dsp;
-        }
-    }
-    __syncthreads();
-    for (int r = 0; r < 2; r++) {
-        const int yy = 2 * blockIdx.x + r;
-        if (yy >= H) break;
-        arrays(r, d2key, selA, selB, disp1s, selBest);
-        int16_t* out = frame_ptr(ws.raw, ws_stride, f) + (size_t)yy * W;
-        for (int x = threadIdx.x; x < W; x += blockDim.x) {
-            int d1 = disp1s[x];
-            if (d1 != kInv) {
-                const int _d = d1 >> 4, d_ = (d1 + 15) >> 4;
-                const int _x = x - _d, x_ = x - d_;
-                auto d2at = [&](int xx) -> int {
-                    const uint32_t kk = d2key[xx];
-                    return kk == kD2Init ? kInv : (int)(0xFFFFu - (kk & 0xFFFFu));
-                };
-                bool badl = false, badr = false;
-                if (_x >= 0 && _x < W) { const int v = d2at(_x); badl = v >= 0 && abs(v - _d) > d.disp12; }
-                if (x_ >= 0 && x_ < W) { const int v = d2at(x_); badr = v >= 0 && abs(v - d_) > d.disp12; }
-                if (badl && badr) d1 = kInv;
-            }
-            out[x] = (int16_t)d1;
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------------
 // A.4.6 post filters
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void cswap(int& a, int& b) { const int t = min(a, b); b = max(a, b); a = t; }
@@ -959,16 +693,6 @@ int launch_paths(const SgbmDims& d, const SgbmWorkspace& ws, size_t ws_stride, i
     dim3 gv((d.mode ? 6 : 3) * cdiv(d.W1, 8), nb);
     { auto k_sgbm_vert_t = k_sgbm_vert<NPR, PAD>; OVO_LAUNCH(k_sgbm_vert_t, gv, dim3(256), 0, st, d, ws, ws_stride); }
     OVO_LAUNCH_CHECK();
-#ifndef OVO_NO_HORIZ2
-    if (NPR == 2) {  // 128-wide disparity range: two rows per warp
-        const size_t smem2 = 2 * (size_t)((6 * d.W + 10 * d.W1 + 15) / 16 * 16) + 16;
-        auto k_sgbm_horiz_t = k_sgbm_horiz2<PAD>;
-        if (smem2 > 48 * 1024) OVO_CUDA(cudaFuncSetAttribute(k_sgbm_horiz_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-        OVO_LAUNCH(k_sgbm_horiz_t, dim3(cdiv(d.H, 2), nb), dim3(64), smem2, st, d, ws, ws_stride);
-        OVO_LAUNCH_CHECK();
-        return 0;
-    }
-#endif
     dim3 gh(d.H, nb);
     const size_t smem = (size_t)d.W * 6 + (size_t)d.W1 * 10 + 16;
     { auto k_sgbm_horiz_t = k_sgbm_horiz<NPR, PAD>;
