@@ -131,8 +131,11 @@ __device__ __forceinline__ void cost_row(const uint2* __restrict__ Lrow, const u
     }
 }
 
+#ifndef OVO_COST_MINB
+#define OVO_COST_MINB 5
+#endif
 template <int SW2, int TX>
-__global__ void __launch_bounds__(kCostThreads) k_sgbm_cost(SgbmDims d, SgbmWorkspace ws, size_t ws_stride) {
+__global__ void __launch_bounds__(kCostThreads, OVO_COST_MINB) k_sgbm_cost(SgbmDims d, SgbmWorkspace ws, size_t ws_stride) {
     constexpr int BS = 2 * SW2 + 1;
     __shared__ uint32_t ring[BS * TX * kCostThreads];
     const int npairs = d.Dp >> 1;
