@@ -51,7 +51,8 @@ struct SgbmDims {
 struct SgbmWorkspace {          // per frame, device pointers
     uint32_t* prep;             // [2 img][2 type][H][W]  byte-packed (v, vmin, vmax, 0)
     int16_t* C;                 // [H][W1][Dp] aggregated BT cost
-    int16_t* Lv;                // [3 or 6][H][W1][Dp] paths from (x-1,y-1), (x,y-1), (x+1,y-1) (+ the three from row y+1 in MODE_HH); Lv[1] doubles as scratch
+    int16_t* Lv;                // [3 or 6][H][W1][Dp] paths from (x-1,y-1), (x,y-1), (x+1,y-1) (+ the three from row y+1 in MODE_HH)
+    int16_t* ckpt;              // [H][2][ceil((W1-W1/2)/K)][Dp] state of the two horizontal sweeps every K cells
     int16_t* raw;               // [H][W] disparity after WTA + LR check
     int16_t* med;               // [H][W] after median
     int32_t* label;             // [H][W] speckle CCL labels

@@ -194,6 +194,14 @@ __device__ __forceinline__ void path_reset(PathState<NPR>& s) {
     s.m = 0;
 }
 
+template <int NPR>
+__device__ __forceinline__ uint32_t vec_min(const uint32_t (&L)[NPR]) {  // min over d (warp-uniform)
+    uint32_t t = L[0];
+#pragma unroll
+    for (int r = 1; r < NPR; r++) t = __vminu2(t, L[r]);
+    return __reduce_min_sync(0xffffffffu, min(t & 0xFFFFu, t >> 16));
+}
+
 template <int NPR, bool PAD>
 __device__ __forceinline__ void path_step(PathState<NPR>& s, const uint32_t (&c)[NPR], const uint32_t (&padmask)[NPR],
                                           uint32_t P1P1, uint32_t P2, bool lane_first, bool lane_last) {
@@ -213,13 +221,9 @@ __device__ __forceinline__ void path_step(PathState<NPR>& s, const uint32_t (&c)
         out[r] = c[r] + (t - mm);
         if (PAD) out[r] |= padmask[r];
     }
-    uint32_t t = out[0];
 #pragma unroll
-    for (int r = 0; r < NPR; r++) {
-        s.L[r] = out[r];
-        if (r) t = __vminu2(t, out[r]);
-    }
-    s.m = __reduce_min_sync(0xffffffffu, min(t & 0xFFFFu, t >> 16));
+    for (int r = 0; r < NPR; r++) s.L[r] = out[r];
+    s.m = vec_min<NPR>(s.L);
 }
 
 template <int NPR>
@@ -289,19 +293,38 @@ __device__ __forceinline__ void vert_line(const SgbmDims& d, const uint32_t* __r
     }
     PathState<NPR> s;
     path_reset<NPR>(s);
+    const ptrdiff_t adv = rowadv + STEP * WPC;
     int y = 0;
     for (; y + 2 * kVertPF <= H; y += kVertPF) {  // every step and every prefetch of this group is in range
+        // a diagonal line wraps at most once per image width: groups that neither wrap nor restart advance by a constant
+        const bool clean = STEP == 0 || (STEP > 0 ? (x != 0 && x + 2 * kVertPF < W1) : (x != W1 - 1 && x - 2 * kVertPF >= 0));
+        if (clean) {
 #pragma unroll
-        for (int i = 0; i < kVertPF; i++) {
-            uint32_t c[NPR];
+            for (int i = 0; i < kVertPF; i++) {
+                uint32_t c[NPR];
 #pragma unroll
-            for (int r = 0; r < NPR; r++) c[r] = cbuf[i][r];
-            ldv<NPR>(cbuf[i], ppf);
-            next_row(xpf, ppf);
-            if (STEP != 0 && x == xreset) path_reset<NPR>(s);
-            path_step<NPR, PAD>(s, c, padmask, P1P1, P2, lane_first, lane_last);
-            stv<NPR>(pl, s.L);
-            next_row(x, pl);
+                for (int r = 0; r < NPR; r++) c[r] = cbuf[i][r];
+                ldv<NPR>(cbuf[i], ppf);
+                ppf += adv;
+                path_step<NPR, PAD>(s, c, padmask, P1P1, P2, lane_first, lane_last);
+                stv<NPR>(pl, s.L);
+                pl += adv;
+            }
+            x += STEP * kVertPF;
+            xpf += STEP * kVertPF;
+        } else {
+#pragma unroll
+            for (int i = 0; i < kVertPF; i++) {
+                uint32_t c[NPR];
+#pragma unroll
+                for (int r = 0; r < NPR; r++) c[r] = cbuf[i][r];
+                ldv<NPR>(cbuf[i], ppf);
+                next_row(xpf, ppf);
+                if (STEP != 0 && x == xreset) path_reset<NPR>(s);
+                path_step<NPR, PAD>(s, c, padmask, P1P1, P2, lane_first, lane_last);
+                stv<NPR>(pl, s.L);
+                next_row(x, pl);
+            }
         }
     }
     for (; y < H; y += kVertPF) {
@@ -342,21 +365,22 @@ __global__ void __launch_bounds__(256) k_sgbm_vert(SgbmDims d, SgbmWorkspace ws,
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Paths 0 and 4 + selection (A.4.4) + LR check (A.4.5).  One CTA (two warps) per row.  Warp 0 runs left -> right,
-// warp 1 right -> left.  In its first half a warp stores T = sat(L1+L2+L3+own) over Lv[1]; after the rendezvous each
-// warp reads the other's T, adds its own path and owns the complete S for the cell.  disp2 is order-independent:
-// min cost, ties to the larger x (= larger d), which is what the reference's right-to-left sweep keeps.
+// Paths 0 and 4 + selection (A.4.4) + LR check (A.4.5).  One CTA (two warps) per row.  Warp 0 runs path 0 left -> right,
+// warp 1 runs path 4 right -> left.  Phase 1: each warp advances its own path over its half of the row reading only C
+// and parks its state every K cells (a checkpoint, 1/K of a volume).  Phase 2: each warp continues into the other
+// half; per K-cell segment it replays the other warp's path forward from the checkpoint (registers only), then walks
+// the segment in its own direction, where S = sat(L1 + L2 + L3 + replayed + own) is complete and selection runs.
+// Every volume is read once per use (C twice, Lv once) and nothing volume-sized is written.  disp2 is
+// order-independent: min cost, ties to the larger x (= larger d), which is what the reference's right-to-left sweep keeps.
 // ------------------------------------------------------------------------------------------------------------
-#ifndef OVO_HOR_PF1
-#define OVO_HOR_PF1 4
-#endif
-#ifndef OVO_HOR_PF2
-#define OVO_HOR_PF2 4
-#endif
 #ifndef OVO_HOR_MINB
-#define OVO_HOR_MINB 1
+#define OVO_HOR_MINB 10
 #endif
-constexpr int kHorPF1 = OVO_HOR_PF1, kHorPF2 = OVO_HOR_PF2;  // register prefetch depth (cells) of the two phases
+#ifndef OVO_HOR_K
+#define OVO_HOR_K 4
+#endif
+template <int NPR>
+__host__ __device__ constexpr int horiz_seg() { return NPR == 4 ? 4 : OVO_HOR_K; }  // K: cells per checkpoint segment
 
 template <int NPR>
 __device__ __forceinline__ uint32_t half_of(const uint32_t (&S)[NPR], int k) {  // k = 2*r + h, compile-time after unrolling
@@ -413,8 +437,201 @@ __device__ __forceinline__ void wta_cell(const uint32_t (&S)[NPR], int lane, con
     }
 }
 
-template <int NPR, bool PAD>
-__global__ void __launch_bounds__(64, OVO_HOR_MINB) k_sgbm_horiz(SgbmDims d, SgbmWorkspace ws, size_t ws_stride) {
+template <int NPR>
+struct HorizRow {          // per-thread view of one row
+    const uint32_t* C;     // + row offset + lane
+    const uint32_t* Lv;    // Lv[0] of the row; Lv[v] is v * vol words further
+    size_t vol;
+    uint32_t* ck_own;      // checkpoints of this warp's phase-1 sweep (segment j at j * 32*NPR words)
+    const uint32_t* ck_oth;
+    int xa, n1, n2;        // first cell and length of the own phase-1 sweep; length of the other warp's
+    uint32_t *selA, *selB;
+    uint16_t* selBest;
+};
+
+#ifndef OVO_HOR_PF1
+#define OVO_HOR_PF1 2
+#endif
+template <int NPR, bool PAD, int DIRX>
+__device__ __forceinline__ void horiz_phase1(const SgbmDims& d, const HorizRow<NPR>& R, PathState<NPR>& s, int lane) {
+    constexpr int WPC = 32 * NPR, K = horiz_seg<NPR>(), DS = DIRX * WPC;
+    constexpr int PF = OVO_HOR_PF1 * K;  // register prefetch depth (cells): this phase is light, so it needs a long run-ahead
+    uint32_t padmask[NPR];
+    make_padmask<NPR>(padmask, lane, d.D);
+    const uint32_t P1P1 = bcast16(d.P1), P2 = d.P2;
+    const bool lane_first = lane == 0, lane_last = lane == 31;
+    const int n1 = R.n1;
+    uint32_t cb[PF][NPR];
+    const uint32_t* pc = R.C + (ptrdiff_t)R.xa * WPC;
+#pragma unroll
+    for (int i = 0; i < PF; i++)
+        if (i < n1) ldv<NPR>(cb[i], pc + i * DS);
+    uint32_t* pk = R.ck_own;  // slot of the checkpoint taken before step k (slot 0, the all-zero start, is never written)
+    for (int k = 0; k < n1; k += PF) {
+        pc += PF * DS;  // now points at the cell PF ahead of step k
+        if (k + 2 * PF <= n1) {
+#pragma unroll
+            for (int i = 0; i < PF; i++) {
+                if (i % K == 0) {
+                    if (k + i) stv<NPR>(pk, s.L);
+                    pk += WPC;
+                }
+                uint32_t c[NPR];
+#pragma unroll
+                for (int r = 0; r < NPR; r++) c[r] = cb[i][r];
+                ldv<NPR>(cb[i], pc + i * DS);
+                path_step<NPR, PAD>(s, c, padmask, P1P1, P2, lane_first, lane_last);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < PF; i++) {
+                if (k + i < n1) {
+                    if (i % K == 0) {
+                        if (k + i) stv<NPR>(pk, s.L);
+                        pk += WPC;
+                    }
+                    uint32_t c[NPR];
+#pragma unroll
+                    for (int r = 0; r < NPR; r++) c[r] = cb[i][r];
+                    if (k + i + PF < n1) ldv<NPR>(cb[i], pc + i * DS);
+                    path_step<NPR, PAD>(s, c, padmask, P1P1, P2, lane_first, lane_last);
+                }
+            }
+        }
+    }
+}
+
+template <int NPR, int DIRX, bool FULL>
+__device__ __forceinline__ void horiz_load_lv(const HorizRow<NPR>& R, ptrdiff_t o0, int cnt, uint32_t (&lv)[3][horiz_seg<NPR>()][NPR]) {
+    constexpr int WPC = 32 * NPR, K = horiz_seg<NPR>(), DS = DIRX * WPC;
+#pragma unroll
+    for (int i = K - 1; i >= 0; i--) {  // the cell consumed first is requested first
+        if (FULL || i < cnt) {
+            ldv<NPR>(lv[0][i], R.Lv + o0 - i * DS);
+            ldv<NPR>(lv[1][i], R.Lv + R.vol + o0 - i * DS);
+            ldv<NPR>(lv[2][i], R.Lv + 2 * R.vol + o0 - i * DS);
+        }
+    }
+}
+
+// One K-cell segment of phase 2.  On entry cb / ckv / lv hold C, the other warp's checkpoint and Lv[0..2] of segment j
+// (requested one segment earlier); on exit they hold those of segment j-1.  FULL: all K cells exist (only the segment
+// next to the rendezvous can be short).
+template <int NPR, bool PAD, bool HH, int DIRX, bool FULL>
+__device__ __forceinline__ void horiz_segment(const SgbmDims& d, const HorizRow<NPR>& R, PathState<NPR>& s, int lane, int j, int cnt,
+                                              uint32_t (&cb)[horiz_seg<NPR>()][NPR], uint32_t (&ckv)[NPR],
+                                              uint32_t (&lv)[3][horiz_seg<NPR>()][NPR], const uint32_t (&padmask)[NPR],
+                                              uint32_t P1P1, uint32_t P2) {
+    constexpr int WPC = 32 * NPR, K = horiz_seg<NPR>(), DS = DIRX * WPC;
+    const bool lane_first = lane == 0, lane_last = lane == 31;
+    // the other warp's cell k (counted along ITS sweep) sits at x = xo - DIRX * k
+    const int xo = (DIRX > 0 ? d.W1 - 1 : 0) - DIRX * (j * K);
+    const ptrdiff_t o0 = (ptrdiff_t)xo * WPC;  // cell i of the segment is at o0 - i * DS
+    uint32_t sv[K][NPR];
+    {
+        // replay the other warp's path over the segment
+        PathState<NPR> o;
+        if (j == 0) {
+            path_reset<NPR>(o);
+        } else {
+#pragma unroll
+            for (int r = 0; r < NPR; r++) o.L[r] = ckv[r];
+            o.m = vec_min<NPR>(o.L);
+        }
+#pragma unroll
+        for (int i = 0; i < K; i++) {
+            if (FULL || i < cnt) {
+                path_step<NPR, PAD>(o, cb[i], padmask, P1P1, P2, lane_first, lane_last);
+#pragma unroll
+                for (int r = 0; r < NPR; r++) sv[i][r] = o.L[r];
+            }
+        }
+#pragma unroll
+        for (int i = K - 1; i >= 0; i--) {
+            if (FULL || i < cnt) {
+#pragma unroll
+                for (int r = 0; r < NPR; r++)
+                    sv[i][r] = __viaddmin_u16x2(__viaddmin_u16x2(__viaddmin_u16x2(lv[0][i][r], lv[1][i][r], kMaxC2), lv[2][i][r], kMaxC2),
+                                                sv[i][r], kMaxC2);
+            }
+        }
+    }
+    if (HH) {  // MODE_HH: the three bottom-up paths Lv[3..5]
+#pragma unroll
+        for (int v = 3; v < 6; v++) {
+#pragma unroll
+            for (int i = K - 1; i >= 0; i--) {
+                if (FULL || i < cnt) {
+                    uint32_t u[NPR];
+                    ldv<NPR>(u, R.Lv + (size_t)v * R.vol + o0 - i * DS);
+#pragma unroll
+                    for (int r = 0; r < NPR; r++) sv[i][r] = __viaddmin_u16x2(sv[i][r], u[r], kMaxC2);
+                }
+            }
+        }
+    }
+    // request everything the next segment (always a full one) needs; it arrives while this one is being walked
+    uint32_t cn[K][NPR], ckn[NPR];
+#pragma unroll
+    for (int r = 0; r < NPR; r++) ckn[r] = 0;
+    if (j > 0) {
+        const uint32_t* pn = R.C + o0 + K * DS;
+#pragma unroll
+        for (int i = 0; i < K; i++) ldv<NPR>(cn[i], pn - i * DS);
+        if (j > 1) ldv<NPR>(ckn, R.ck_oth + (size_t)(j - 1) * WPC);
+        horiz_load_lv<NPR, DIRX, true>(R, o0 + K * DS, K, lv);
+    }
+    // own path over the segment, in the own direction (= the other's, reversed)
+#pragma unroll
+    for (int i = K - 1; i >= 0; i--) {
+        if (FULL || i < cnt) {
+            path_step<NPR, PAD>(s, cb[i], padmask, P1P1, P2, lane_first, lane_last);
+            uint32_t S[NPR];
+#pragma unroll
+            for (int r = 0; r < NPR; r++) S[r] = __viaddmin_u16x2(sv[i][r], s.L[r], kMaxC2);
+            wta_cell<NPR, PAD>(S, lane, d, xo - DIRX * i, R.selA, R.selB, R.selBest);
+        }
+    }
+    if (j > 0) {
+#pragma unroll
+        for (int i = 0; i < K; i++)
+#pragma unroll
+            for (int r = 0; r < NPR; r++) cb[i][r] = cn[i][r];
+#pragma unroll
+        for (int r = 0; r < NPR; r++) ckv[r] = ckn[r];
+    }
+}
+
+template <int NPR, bool PAD, bool HH, int DIRX>
+__device__ __forceinline__ void horiz_phase2(const SgbmDims& d, const HorizRow<NPR>& R, PathState<NPR>& s, int lane) {
+    constexpr int WPC = 32 * NPR, K = horiz_seg<NPR>(), DS = DIRX * WPC;
+    const int n2 = R.n2;
+    if (n2 <= 0) return;
+    uint32_t padmask[NPR];
+    make_padmask<NPR>(padmask, lane, d.D);
+    const uint32_t P1P1 = bcast16(d.P1), P2 = d.P2;
+    int j = (n2 + K - 1) / K - 1;
+    int cnt = n2 - j * K;
+    uint32_t cb[K][NPR], ckv[NPR], lv[3][K][NPR];
+#pragma unroll
+    for (int r = 0; r < NPR; r++) ckv[r] = 0;
+    {
+        const ptrdiff_t o0 = (ptrdiff_t)((DIRX > 0 ? d.W1 - 1 : 0) - DIRX * (j * K)) * WPC;
+#pragma unroll
+        for (int i = 0; i < K; i++)
+            if (i < cnt) ldv<NPR>(cb[i], R.C + o0 - i * DS);
+        if (j > 0) ldv<NPR>(ckv, R.ck_oth + (size_t)j * WPC);
+        horiz_load_lv<NPR, DIRX, false>(R, o0, cnt, lv);
+    }
+    if (cnt < K) {
+        horiz_segment<NPR, PAD, HH, DIRX, false>(d, R, s, lane, j, cnt, cb, ckv, lv, padmask, P1P1, P2);
+        j--;
+    }
+    for (; j >= 0; j--) horiz_segment<NPR, PAD, HH, DIRX, true>(d, R, s, lane, j, K, cb, ckv, lv, padmask, P1P1, P2);
+}
+
+template <int NPR, bool PAD, bool HH>
+__global__ void __launch_bounds__(64, NPR == 4 ? 6 : OVO_HOR_MINB) k_sgbm_horiz(SgbmDims d, SgbmWorkspace ws, size_t ws_stride) {
     OVO_DYN_SMEM(uint32_t, hsm);
     uint32_t* d2key = hsm;                                        // [W]
     uint32_t* selA = hsm + d.W;                                   // [W1] minS | runner-up << 16
@@ -424,118 +641,35 @@ __global__ void __launch_bounds__(64, OVO_HOR_MINB) k_sgbm_horiz(SgbmDims d, Sgb
     const int y = blockIdx.x, f = blockIdx.y;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int W = d.W, W1 = d.W1, H = d.H;
-    constexpr int WPC = 32 * NPR;
+    constexpr int WPC = 32 * NPR, K = horiz_seg<NPR>();
     for (int i = threadIdx.x; i < W; i += blockDim.x) {
         d2key[i] = kD2Init;
         disp1s[i] = (int16_t)kInv;
     }
     __syncthreads();
 
-    const size_t rowoff = (size_t)y * W1 * WPC + lane * NPR;
-    const size_t vol = (size_t)H * W1 * WPC;
-    const uint32_t* C = reinterpret_cast<const uint32_t*>(frame_ptr(ws.C, ws_stride, f)) + rowoff;
-    const uint32_t* L1 = reinterpret_cast<const uint32_t*>(frame_ptr(ws.Lv, ws_stride, f)) + rowoff;
-    uint32_t* T = const_cast<uint32_t*>(L1) + vol;  // Lv[1] doubles as the rendezvous scratch
-    const uint32_t* L3 = L1 + 2 * vol;
-
-    uint32_t padmask[NPR];
-    make_padmask<NPR>(padmask, lane, d.D);
-    const uint32_t P1P1 = bcast16(d.P1), P2 = d.P2;
-    const bool lane_first = lane == 0, lane_last = lane == 31;
     const int mid = W1 >> 1;
-    const int dirx = wid == 0 ? 1 : -1;
-    const int xa = wid == 0 ? 0 : W1 - 1;               // first cell of phase 1
-    const int n1 = wid == 0 ? mid : W1 - mid;           // cells in phase 1
-    const int n2 = W1 - n1;                             // cells in phase 2
-    const ptrdiff_t dstep = dirx * WPC;                 // word step between consecutive cells of this warp
+    const int sph = (W1 - mid + K - 1) / K;  // checkpoint slots per half row
+    HorizRow<NPR> R;
+    const size_t rowoff = (size_t)y * W1 * WPC + lane * NPR;
+    R.vol = (size_t)H * W1 * WPC;
+    R.C = reinterpret_cast<const uint32_t*>(frame_ptr(ws.C, ws_stride, f)) + rowoff;
+    R.Lv = reinterpret_cast<const uint32_t*>(frame_ptr(ws.Lv, ws_stride, f)) + rowoff;
+    uint32_t* ck = reinterpret_cast<uint32_t*>(frame_ptr(ws.ckpt, ws_stride, f)) + (size_t)y * 2 * sph * WPC + lane * NPR;
+    R.ck_own = ck + (size_t)wid * sph * WPC;
+    R.ck_oth = ck + (size_t)(1 - wid) * sph * WPC;
+    R.xa = wid == 0 ? 0 : W1 - 1;
+    R.n1 = wid == 0 ? mid : W1 - mid;
+    R.n2 = W1 - R.n1;
+    R.selA = selA; R.selB = selB; R.selBest = selBest;
 
     PathState<NPR> s;
     path_reset<NPR>(s);
-    // ---- phase 1: T = sat(L1 + L2 + L3 + own)
-    {
-        uint32_t cb[kHorPF1][NPR], l1[kHorPF1][NPR], l2[kHorPF1][NPR], l3[kHorPF1][NPR];
-        const uint32_t *pc = C + xa * WPC, *p1 = L1 + xa * WPC, *p3 = L3 + xa * WPC;
-        const uint32_t* p2 = T + xa * WPC;
-        uint32_t* po = T + xa * WPC;
-#pragma unroll
-        for (int i = 0; i < kHorPF1; i++) {
-            if (i < n1) { ldv<NPR>(cb[i], pc); ldv<NPR>(l1[i], p1); ldv<NPR>(l2[i], p2); ldv<NPR>(l3[i], p3); }
-            pc += dstep; p1 += dstep; p2 += dstep; p3 += dstep;
-        }
-        const bool hh = d.mode != 0;  // MODE_HH: add the three bottom-up paths Lv[3..5] (read late, not prefetched)
-        const uint32_t* pu = L1 + 3 * vol + xa * WPC;
-        auto body = [&](int i, bool pf) {
-            uint32_t c[NPR], sv[NPR];
-#pragma unroll
-            for (int r = 0; r < NPR; r++) {
-                c[r] = cb[i][r];
-                sv[r] = __viaddmin_u16x2(__viaddmin_u16x2(l1[i][r], l2[i][r], kMaxC2), l3[i][r], kMaxC2);
-            }
-            if (hh) {
-#pragma unroll
-                for (int v = 0; v < 3; v++) {
-                    uint32_t u[NPR];
-                    ldv<NPR>(u, pu + (size_t)v * vol);
-#pragma unroll
-                    for (int r = 0; r < NPR; r++) sv[r] = __viaddmin_u16x2(sv[r], u[r], kMaxC2);
-                }
-                pu += dstep;
-            }
-            if (pf) { ldv<NPR>(cb[i], pc); ldv<NPR>(l1[i], p1); ldv<NPR>(l2[i], p2); ldv<NPR>(l3[i], p3); }
-            pc += dstep; p1 += dstep; p2 += dstep; p3 += dstep;
-            path_step<NPR, PAD>(s, c, padmask, P1P1, P2, lane_first, lane_last);
-#pragma unroll
-            for (int r = 0; r < NPR; r++) sv[r] = __viaddmin_u16x2(sv[r], s.L[r], kMaxC2);
-            stv<NPR>(po, sv);
-            po += dstep;
-        };
-        int k = 0;
-        for (; k + 2 * kHorPF1 <= n1; k += kHorPF1) {
-#pragma unroll
-            for (int i = 0; i < kHorPF1; i++) body(i, true);
-        }
-        for (; k < n1; k += kHorPF1) {
-#pragma unroll
-            for (int i = 0; i < kHorPF1; i++)
-                if (k + i < n1) body(i, k + i + kHorPF1 < n1);
-        }
-    }
+    if (wid == 0) horiz_phase1<NPR, PAD, 1>(d, R, s, lane);
+    else horiz_phase1<NPR, PAD, -1>(d, R, s, lane);
     __syncthreads();
-    // ---- phase 2: S = sat(T_other + own) -> selection
-    {
-        const int xb = xa + dirx * n1;
-        uint32_t cb[kHorPF2][NPR], tb[kHorPF2][NPR];
-        const uint32_t *pc = C + xb * WPC, *pt = T + xb * WPC;
-#pragma unroll
-        for (int i = 0; i < kHorPF2; i++) {
-            if (i < n2) { ldv<NPR>(cb[i], pc); ldv<NPR>(tb[i], pt); }
-            pc += dstep; pt += dstep;
-        }
-        int x1 = xb;
-        if (n1 == 0) path_reset<NPR>(s);
-        auto body = [&](int i, bool pf) {
-            uint32_t c[NPR], S[NPR];
-#pragma unroll
-            for (int r = 0; r < NPR; r++) { c[r] = cb[i][r]; S[r] = tb[i][r]; }
-            if (pf) { ldv<NPR>(cb[i], pc); ldv<NPR>(tb[i], pt); }
-            pc += dstep; pt += dstep;
-            path_step<NPR, PAD>(s, c, padmask, P1P1, P2, lane_first, lane_last);
-#pragma unroll
-            for (int r = 0; r < NPR; r++) S[r] = __viaddmin_u16x2(S[r], s.L[r], kMaxC2);
-            wta_cell<NPR, PAD>(S, lane, d, x1, selA, selB, selBest);
-            x1 += dirx;
-        };
-        int k = 0;
-        for (; k + 2 * kHorPF2 <= n2; k += kHorPF2) {
-#pragma unroll
-            for (int i = 0; i < kHorPF2; i++) body(i, true);
-        }
-        for (; k < n2; k += kHorPF2) {
-#pragma unroll
-            for (int i = 0; i < kHorPF2; i++)
-                if (k + i < n2) body(i, k + i + kHorPF2 < n2);
-        }
-    }
+    if (wid == 0) horiz_phase2<NPR, PAD, HH, 1>(d, R, s, lane);
+    else horiz_phase2<NPR, PAD, HH, -1>(d, R, s, lane);
     __syncthreads();
     // ---- uniqueness, sub-pixel refinement and disp2 (A.4.4), data-parallel over the row
     {
@@ -698,9 +832,15 @@ int launch_paths(const SgbmDims& d, const SgbmWorkspace& ws, size_t ws_stride, i
     OVO_LAUNCH_CHECK();
     dim3 gh(d.H, nb);
     const size_t smem = (size_t)d.W * 6 + (size_t)d.W1 * 10 + 16;
-    { auto k_sgbm_horiz_t = k_sgbm_horiz<NPR, PAD>;
-      if (smem > 48 * 1024) OVO_CUDA(cudaFuncSetAttribute(k_sgbm_horiz_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      OVO_LAUNCH(k_sgbm_horiz_t, gh, dim3(64), smem, st, d, ws, ws_stride); }
+    if (d.mode) {
+        auto k_sgbm_horiz_t = k_sgbm_horiz<NPR, PAD, true>;
+        if (smem > 48 * 1024) OVO_CUDA(cudaFuncSetAttribute(k_sgbm_horiz_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OVO_LAUNCH(k_sgbm_horiz_t, gh, dim3(64), smem, st, d, ws, ws_stride);
+    } else {
+        auto k_sgbm_horiz_t = k_sgbm_horiz<NPR, PAD, false>;
+        if (smem > 48 * 1024) OVO_CUDA(cudaFuncSetAttribute(k_sgbm_horiz_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OVO_LAUNCH(k_sgbm_horiz_t, gh, dim3(64), smem, st, d, ws, ws_stride);
+    }
     OVO_LAUNCH_CHECK();
     return 0;
 }
@@ -717,10 +857,17 @@ int launch_cost(const SgbmDims& d, const SgbmWorkspace& ws, size_t ws_stride, in
 
 }  // namespace
 
+// checkpoints of the horizontal sweeps: per row 2 x ceil((W1 - W1/2) / K) cost vectors (K = 4 for Dp = 256, else 8)
+static size_t ckpt_bytes(const SgbmDims& d) {
+    const int K = d.Dp == 256 ? horiz_seg<4>() : horiz_seg<2>();
+    const int sph = (d.W1 - (d.W1 >> 1) + K - 1) / K;
+    return align_up((size_t)d.H * 2 * sph * d.Dp * 2, 256);
+}
+
 size_t sgbm_workspace_bytes(const SgbmDims& d) {
     const size_t vol = align_up((size_t)d.H * d.W1 * d.Dp * 2, 256);
     const size_t img = align_up((size_t)d.H * d.W * 4, 256);
-    return align_up(4 * img /*prep*/ + (d.mode ? 7 : 4) * vol /*C + Lv[3]*/ + 4 * img /*raw, med (i16) + label, csize (i32) -> 2*0.5+2 = 3 img*/, 256);
+    return align_up(4 * img /*prep*/ + (d.mode ? 7 : 4) * vol /*C + Lv[3]*/ + ckpt_bytes(d) + 4 * img /*raw, med (i16) + label, csize (i32) -> 2*0.5+2 = 3 img*/, 256);
 }
 
 void sgbm_carve(const SgbmDims& d, uint8_t* base, SgbmWorkspace* ws) {
@@ -730,6 +877,7 @@ void sgbm_carve(const SgbmDims& d, uint8_t* base, SgbmWorkspace* ws) {
     ws->prep = reinterpret_cast<uint32_t*>(p); p += 4 * img;
     ws->C = reinterpret_cast<int16_t*>(p); p += vol;
     ws->Lv = reinterpret_cast<int16_t*>(p); p += (d.mode ? 6 : 3) * vol;
+    ws->ckpt = reinterpret_cast<int16_t*>(p); p += ckpt_bytes(d);
     ws->raw = reinterpret_cast<int16_t*>(p); p += img / 2;
     ws->med = reinterpret_cast<int16_t*>(p); p += img / 2;
     ws->label = reinterpret_cast<int32_t*>(p); p += img;
