@@ -74,17 +74,20 @@ struct OrbLevel {
     int nfeat;         // feature budget
     float scale, inv;  // scale_l, 1/scale_l (float32)
     int row_off;       // offset of this level's first row inside per-row arrays
+    int mw, moff;      // candidate bit mask: 32-bit words per row, word offset of the level
 };
 struct OrbDims {
     int W, H, nfeatures;
-    int total_px, total_rows, cand_cap, kp_cap;
+    int total_px, total_rows, total_mwords, cand_cap, kp_cap;
     OrbLevel lv[ORB_NLEVELS];
+    int fast_tiles[ORB_NLEVELS + 1], blur_tiles[ORB_NLEVELS + 1];  // first flat tile index of each level (+ total)
 };
 void orb_make_dims(int W, int H, int nfeatures, OrbDims* d);
 
 struct OrbWorkspace {           // per frame, device pointers
     uint8_t *pyr, *maskpyr, *score, *blur;  // [total_px] each
-    int32_t *row_count, *row_offset;         // [total_rows]
+    int32_t* row_offset;                     // [total_rows] candidates before the row, over all levels
+    uint32_t* candmask;                      // [total_mwords] one bit per pixel: NMS + border + mask survivor
     int32_t* lvl_count;                      // [8] candidates per level (+ [8] offsets)
     int32_t* cand_xy;                        // [cand_cap] packed (y<<16 | x)
     float* cand_resp;                        // [cand_cap][2] (FAST score, Harris response)

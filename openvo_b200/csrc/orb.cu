@@ -78,7 +78,7 @@ __device__ __forceinline__ int arc9_max_of_min(const int (&v)[16]) {
     return best;
 }
 
-constexpr int kFastTX = 32, kFastTY = 8;
+constexpr int kFastTX = 32, kFastTY = 16;  // tile of the fused FAST + NMS kernel (one 32-bit candidate word per tile row)
 
 __device__ __forceinline__ void fast_ring(const uint8_t (*tile)[kFastTX + 8], int cx, int cy, int (&v)[16]) {
     const int c = tile[cy][cx];
@@ -88,164 +88,218 @@ __device__ __forceinline__ void fast_ring(const uint8_t (*tile)[kFastTX + 8], in
     v[12] = c - tile[cy][cx - 3];     v[13] = c - tile[cy + 1][cx - 3]; v[14] = c - tile[cy + 2][cx - 2]; v[15] = c - tile[cy + 3][cx - 1];
 }
 
-// Two passes per tile so that the expensive score (max over arcs of min over 9) runs densely on corner pixels only: pass A is
-// the 9-contiguous test on brighter / darker bit masks for every pixel (non-corners store 0), corners are queued in shared
-// memory; pass B scores the queue.
-__global__ void __launch_bounds__(kFastTX* kFastTY) k_orb_fast(OrbDims d, OrbWorkspace ws, size_t ws_stride) {
-    __shared__ uint8_t tile[kFastTY + 6][kFastTX + 8];
-    __shared__ uint16_t queue[kFastTX * kFastTY];
+// Tiles of every level are numbered consecutively (level-major, then row-major), so one grid covers the whole pyramid
+// without empty CTAs.  OrbDims carries the per-level prefix for the two tile shapes in use (FAST, blur).
+__device__ __forceinline__ void orb_flat_tile(const int (&off)[ORB_NLEVELS + 1], const OrbDims& d, int TX, int t, int& level, int& tx, int& ty) {
+    int l = 0;
+#pragma unroll
+    for (int k = 1; k < ORB_NLEVELS; k++) l += (t >= off[k]) ? 1 : 0;
+    const int nx = (d.lv[l].w + TX - 1) / TX;
+    t -= off[l];
+    level = l;
+    ty = t / nx;
+    tx = t - ty * nx;
+}
+
+// FAST score + 3x3 NMS + border + mask, fused per 32x16 tile.  Pass A: the 9-contiguous test on brighter / darker bit
+// masks for every pixel of the tile plus a one-pixel apron (non-corners score 0), corners are queued in shared memory;
+// pass B scores the queue (max over arcs of min over 9, the expensive part, runs densely on corners only); pass C: a pixel
+// is a candidate when its score strictly beats its 8 neighbours, it lies inside the 31-pixel border and the mask is set.
+// Output: one bit per pixel (a 32-bit word per tile row, bit i = column x0 + i) and the score byte of each candidate.
+__global__ void __launch_bounds__(256) k_orb_fast_nms(OrbDims d, OrbWorkspace ws, size_t ws_stride, int has_mask) {
+    constexpr int TX = kFastTX, TY = kFastTY, SW = TX + 2, SH = TY + 2;
+    __shared__ uint8_t tile[TY + 8][kFastTX + 8];
+    __shared__ uint8_t sc[SH][SW + 2];
+    __shared__ uint16_t queue[SW * SH];
     __shared__ int nq;
-    const int level = blockIdx.z % ORB_NLEVELS, f = blockIdx.z / ORB_NLEVELS;
+    int level, bx, by;
+    orb_flat_tile(d.fast_tiles, d, TX, blockIdx.x, level, bx, by);
+    const int f = blockIdx.y;
     const OrbLevel L = d.lv[level];
-    const int x0 = blockIdx.x * kFastTX, y0 = blockIdx.y * kFastTY;
-    if (x0 >= L.w || y0 >= L.h) return;
+    const int x0 = bx * TX, y0 = by * TY;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint32_t* cm = fptr(ws.candmask, ws_stride, f) + L.moff;
+    // candidates live in [kEdge, w - kEdge) x [kEdge, h - kEdge): tiles outside only clear their words
+    const bool live = x0 < L.w - kEdge && x0 + TX > kEdge && y0 < L.h - kEdge && y0 + TY > kEdge;
+    if (!live) {
+        if (tid < TY && y0 + tid < L.h) cm[(size_t)(y0 + tid) * L.mw + bx] = 0u;
+        return;
+    }
     const uint8_t* img = fptr(ws.pyr, ws_stride, f) + L.off;
-    uint8_t* out = fptr(ws.score, ws_stride, f) + L.off;
-    const int tid = threadIdx.y * kFastTX + threadIdx.x;
     if (tid == 0) nq = 0;
-    for (int i = tid; i < (kFastTY + 6) * (kFastTX + 6); i += kFastTX * kFastTY) {
-        const int ty = i / (kFastTX + 6), tx = i % (kFastTX + 6);
-        const int gx = min(max(x0 + tx - 3, 0), L.w - 1), gy = min(max(y0 + ty - 3, 0), L.h - 1);
+    for (int i = tid; i < (TY + 8) * (TX + 8); i += 256) {
+        const int ty = i / (TX + 8), tx = i - ty * (TX + 8);
+        const int gx = min(max(x0 + tx - 4, 0), L.w - 1), gy = min(max(y0 + ty - 4, 0), L.h - 1);
         tile[ty][tx] = img[(size_t)gy * L.w + gx];
     }
     __syncthreads();
-    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-    if (x < L.w && y < L.h) {
+    // pass A over the tile + apron; scores outside [kEdge-1, w-kEdge] are never read by a candidate, so they are skipped
+    for (int i0 = 0; i0 < SW * SH; i0 += 256) {
+        const int i = i0 + tid;
         bool corner = false;
-        if (x >= 3 && x < L.w - 3 && y >= 3 && y < L.h - 3) {
-            int v[16];
-            fast_ring(tile, threadIdx.x + 3, threadIdx.y + 3, v);
-            uint32_t mb = 0, md = 0;
+        int sx = 0, sy = 0;
+        if (i < SW * SH) {
+            sy = i / SW;
+            sx = i - sy * SW;
+            const int x = x0 - 1 + sx, y = y0 - 1 + sy;
+            if (x >= kEdge - 1 && x <= L.w - kEdge && y >= kEdge - 1 && y <= L.h - kEdge) {
+                int v[16];
+                fast_ring(tile, sx + 3, sy + 3, v);  // v[k] = centre - ring[k]
+                uint32_t mb = 0, md = 0;
 #pragma unroll
-            for (int k = 0; k < 16; k++) {
-                mb |= (v[k] > kFastT ? 1u : 0u) << k;
-                md |= (v[k] < -kFastT ? 1u : 0u) << k;
+                for (int k = 0; k < 16; k++) {
+                    if (v[k] > kFastT) mb |= 1u << k;
+                    if (v[k] < -kFastT) md |= 1u << k;
+                }
+                auto has9 = [](uint32_t m) {
+                    m |= m << 16;
+                    uint32_t t = m & (m >> 1);
+                    t &= t >> 2;
+                    t &= t >> 4;
+                    t &= m >> 8;
+                    return (t & 0xFFFFu) != 0;
+                };
+                corner = has9(mb) || has9(md);
             }
-            auto has9 = [](uint32_t m) {
-                m |= m << 16;
-                uint32_t t = m & (m >> 1);
-                t &= t >> 2;
-                t &= t >> 4;
-                t &= m >> 8;
-                return (t & 0xFFFFu) != 0;
-            };
-            corner = has9(mb) || has9(md);
+            if (!corner) sc[sy][sx] = 0;
         }
-        if (corner) queue[atomicAdd(&nq, 1)] = (uint16_t)tid;
-        else out[(size_t)y * L.w + x] = 0;
+        const uint32_t bal = __ballot_sync(0xffffffffu, corner);
+        if (bal) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&nq, __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (corner) queue[base + __popc(bal & ((1u << lane) - 1))] = (uint16_t)i;
+        }
     }
     __syncthreads();
     const int n = nq;
-    for (int i = tid; i < n; i += kFastTX * kFastTY) {
-        const int t = queue[i], tx = t % kFastTX, ty = t / kFastTX;
+    for (int i = tid; i < n; i += 256) {
+        const int t = queue[i], sy = t / SW, sx = t - sy * SW;
         int v[16], nv[16];
-        fast_ring(tile, tx + 3, ty + 3, v);
+        fast_ring(tile, sx + 3, sy + 3, v);
 #pragma unroll
         for (int k = 0; k < 16; k++) nv[k] = -v[k];
         const int m = max(arc9_max_of_min(v), arc9_max_of_min(nv));
-        out[(size_t)(y0 + ty) * L.w + x0 + tx] = (uint8_t)(m - 1);  // largest threshold for which the pixel is still a corner
+        sc[sy][sx] = (uint8_t)(m - 1);  // largest threshold for which the pixel is still a corner
     }
-}
-
-// ---- NMS + mask + border, emitted in raster order --------------------------------------------------------------------------
-__device__ __forceinline__ bool is_candidate(const uint8_t* sc, const uint8_t* mk, int w, int x, int y) {
-    const uint8_t* p = sc + (size_t)y * w + x;
-    const int s = p[0];
-    if (s == 0) return false;
-    if (p[-1] >= s || p[1] >= s || p[-w - 1] >= s || p[-w] >= s || p[-w + 1] >= s || p[w - 1] >= s || p[w] >= s || p[w + 1] >= s)
-        return false;
-    return mk == nullptr || mk[(size_t)y * w + x] != 0;
-}
-
-template <bool EMIT>
-__global__ void __launch_bounds__(256) k_orb_nms(OrbDims d, OrbWorkspace ws, size_t ws_stride, int has_mask) {
-    const int level = blockIdx.y, f = blockIdx.z;
-    const OrbLevel L = d.lv[level];
-    const int lane = threadIdx.x & 31;
-    const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (y >= L.h) return;
-    int32_t* row_count = fptr(ws.row_count, ws_stride, f) + L.row_off;
-    const bool inside = y >= kEdge && y < L.h - kEdge;
-    const uint8_t* sc = fptr(ws.score, ws_stride, f) + L.off;
+    __syncthreads();
     const uint8_t* mk = has_mask ? fptr(ws.maskpyr, ws_stride, f) + L.off : nullptr;
-    int base = 0;
-    int32_t* cxy = nullptr;
-    float* cresp = nullptr;
-    if (EMIT) {
-        const int32_t* lvl = fptr(ws.lvl_count, ws_stride, f);
-        base = lvl[ORB_NLEVELS + level] + fptr(ws.row_offset, ws_stride, f)[L.row_off + y];
-        cxy = fptr(ws.cand_xy, ws_stride, f);
-        cresp = fptr(ws.cand_resp, ws_stride, f);
-    }
-    int count = 0;
-    if (inside) {
-        for (int xb = kEdge; xb < L.w - kEdge; xb += 32) {
-            const int x = xb + lane;
-            const bool c = x < L.w - kEdge && is_candidate(sc, mk, L.w, x, y);
-            const uint32_t bal = __ballot_sync(0xffffffffu, c);
-            if (EMIT && c) {
-                const int idx = base + count + __popc(bal & ((1u << lane) - 1));
-                if (idx < d.cand_cap) {
-                    cxy[idx] = (y << 16) | x;
-                    cresp[2 * idx] = (float)sc[(size_t)y * L.w + x];
-                }
-            }
-            count += __popc(bal);
+    uint8_t* out = fptr(ws.score, ws_stride, f) + L.off;
+#pragma unroll
+    for (int rr = 0; rr < TY / 8; rr++) {
+        const int ty = wid + rr * 8, x = x0 + lane, y = y0 + ty;
+        if (y >= L.h) continue;  // warp-uniform
+        bool c = false;
+        const int s = sc[ty + 1][lane + 1];
+        if (s != 0 && x >= kEdge && x < L.w - kEdge && y >= kEdge && y < L.h - kEdge) {
+            const uint8_t *r0 = &sc[ty][lane], *r1 = &sc[ty + 1][lane], *r2 = &sc[ty + 2][lane];
+            c = r0[0] < s && r0[1] < s && r0[2] < s && r1[0] < s && r1[2] < s && r2[0] < s && r2[1] < s && r2[2] < s;
+            if (c && mk) c = mk[(size_t)y * L.w + x] != 0;
         }
+        const uint32_t bal = __ballot_sync(0xffffffffu, c);
+        if (lane == 0) cm[(size_t)y * L.mw + bx] = bal;
+        if (c) out[(size_t)y * L.w + x] = (uint8_t)s;
     }
-    if (!EMIT && lane == 0) row_count[y] = count;
 }
 
-// one CTA per frame: exclusive scan of the row counts of each level; lvl_count[0..7] = per-level totals,
-// lvl_count[8..15] = level base offsets, lvl_count[16] = total
+// one CTA per frame: candidates per row (popcount of the row's mask words) and their exclusive scan over all rows of all
+// levels (rows are numbered level-major, so raster order inside a level is kept).  row_offset[r] = candidates before row r;
+// lvl_count[0..7] = per-level totals, lvl_count[8..15] = level base offsets, lvl_count[16] = total
 __global__ void __launch_bounds__(1024) k_orb_scan(OrbDims d, OrbWorkspace ws, size_t ws_stride) {
     __shared__ int warp_sums[32];
     __shared__ int carry;
     const int f = blockIdx.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int32_t* rc = fptr(ws.row_count, ws_stride, f);
+    const uint32_t* cm = fptr(ws.candmask, ws_stride, f);
     int32_t* ro = fptr(ws.row_offset, ws_stride, f);
     int32_t* lvl = fptr(ws.lvl_count, ws_stride, f);
-    int lvl_base = 0;
-    for (int l = 0; l < ORB_NLEVELS; l++) {
-        const OrbLevel L = d.lv[l];
-        if (threadIdx.x == 0) carry = 0;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int r0 = 0; r0 < d.total_rows; r0 += 1024) {
+        const int r = r0 + threadIdx.x;
+        int v = 0;
+        if (r < d.total_rows) {
+            int l = 0;
+#pragma unroll
+            for (int k = 1; k < ORB_NLEVELS; k++) l += (r >= d.lv[k].row_off) ? 1 : 0;
+            const OrbLevel L = d.lv[l];
+            const int y = r - L.row_off;
+            if (y >= kEdge && y < L.h - kEdge) {
+                const uint32_t* w = cm + L.moff + (size_t)y * L.mw;
+                for (int i = 0; i < L.mw; i++) v += __popc(w[i]);
+            }
+        }
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_sums[wid] = incl;
         __syncthreads();
-        for (int r0 = 0; r0 < L.h; r0 += 1024) {
-            const int r = r0 + threadIdx.x;
-            const int v = r < L.h ? rc[L.row_off + r] : 0;
-            int incl = v;
+        if (wid == 0) {
+            int s = warp_sums[lane];
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
+                const int t = __shfl_up_sync(0xffffffffu, s, o);
+                if (lane >= o) s += t;
             }
-            if (lane == 31) warp_sums[wid] = incl;
-            __syncthreads();
-            if (wid == 0) {
-                int s = warp_sums[lane];
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int t = __shfl_up_sync(0xffffffffu, s, o);
-                    if (lane >= o) s += t;
-                }
-                warp_sums[lane] = s;
-            }
-            __syncthreads();
-            const int before = carry + (wid ? warp_sums[wid - 1] : 0) + incl - v;
-            if (r < L.h) ro[L.row_off + r] = before;
-            __syncthreads();
-            if (threadIdx.x == 1023) carry = before + v;
-            __syncthreads();
+            warp_sums[lane] = s;
         }
-        if (threadIdx.x == 0) {
-            lvl[l] = carry;
-            lvl[ORB_NLEVELS + l] = lvl_base;
-        }
-        lvl_base += carry;
+        __syncthreads();
+        const int before = carry + (wid ? warp_sums[wid - 1] : 0) + incl - v;
+        if (r < d.total_rows) ro[r] = before;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = before + v;
         __syncthreads();
     }
-    if (threadIdx.x == 0) lvl[2 * ORB_NLEVELS] = lvl_base;
+    if (threadIdx.x < ORB_NLEVELS) {
+        const int l = threadIdx.x;
+        const int b0 = ro[d.lv[l].row_off], b1 = l + 1 < ORB_NLEVELS ? ro[d.lv[l + 1].row_off] : carry;
+        lvl[l] = b1 - b0;
+        lvl[ORB_NLEVELS + l] = b0;
+    }
+    if (threadIdx.x == 0) lvl[2 * ORB_NLEVELS] = carry;
+}
+
+// candidates in raster order: one warp per row walks the row's mask words
+__global__ void __launch_bounds__(256) k_orb_emit(OrbDims d, OrbWorkspace ws, size_t ws_stride) {
+    const int lane = threadIdx.x & 31, f = blockIdx.y;
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= d.total_rows) return;
+    int l = 0;
+#pragma unroll
+    for (int k = 1; k < ORB_NLEVELS; k++) l += (r >= d.lv[k].row_off) ? 1 : 0;
+    const OrbLevel L = d.lv[l];
+    const int y = r - L.row_off;
+    if (y < kEdge || y >= L.h - kEdge) return;
+    const uint32_t* w = fptr(ws.candmask, ws_stride, f) + L.moff + (size_t)y * L.mw;
+    const uint8_t* sc = fptr(ws.score, ws_stride, f) + L.off + (size_t)y * L.w;
+    int32_t* cxy = fptr(ws.cand_xy, ws_stride, f);
+    float* cresp = fptr(ws.cand_resp, ws_stride, f);
+    int base = fptr(ws.row_offset, ws_stride, f)[r];
+    for (int i0 = 0; i0 < L.mw; i0 += 32) {
+        uint32_t bits = i0 + lane < L.mw ? w[i0 + lane] : 0u;
+        const int cnt = __popc(bits);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        int idx = base + incl - cnt;
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const int x = (i0 + lane) * 32 + b;
+            if (idx < d.cand_cap) {
+                cxy[idx] = (y << 16) | x;
+                cresp[2 * idx] = (float)sc[x];
+            }
+            idx++;
+        }
+        base += __shfl_sync(0xffffffffu, incl, 31);
+    }
 }
 
 __device__ __forceinline__ int cand_level(const int32_t* lvl, int i) {
@@ -300,10 +354,11 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 __global__ void __launch_bounds__(256) k_orb_blur(OrbDims d, OrbWorkspace ws, size_t ws_stride) {
     __shared__ uint8_t src[kBlurTY + 6][kBlurTX + 8];
     __shared__ float rows[kBlurTY + 6][kBlurTX];
-    const int level = blockIdx.z % ORB_NLEVELS, f = blockIdx.z / ORB_NLEVELS;
+    int level, bx, by;
+    orb_flat_tile(d.blur_tiles, d, kBlurTX, blockIdx.x, level, bx, by);
+    const int f = blockIdx.y;
     const OrbLevel L = d.lv[level];
-    const int x0 = blockIdx.x * kBlurTX, y0 = blockIdx.y * kBlurTY;
-    if (x0 >= L.w || y0 >= L.h) return;
+    const int x0 = bx * kBlurTX, y0 = by * kBlurTY;
     const uint8_t* img = fptr(ws.pyr, ws_stride, f) + L.off;
     for (int i = threadIdx.x; i < (kBlurTY + 6) * (kBlurTX + 6); i += 256) {
         const int ty = i / (kBlurTX + 6), tx = i % (kBlurTX + 6);
@@ -438,7 +493,7 @@ void orb_make_dims(int W, int H, int nfeatures, OrbDims* d) {
     // SURVEY.md A.1.1 — float32 arithmetic exactly as OpenCV's ORB_Impl does it
     d->W = W; d->H = H; d->nfeatures = nfeatures;
     const float scaleFactor = 1.2f;
-    int off = 0, rows = 0;
+    int off = 0, rows = 0, mwords = 0;
     for (int l = 0; l < ORB_NLEVELS; l++) {
         OrbLevel& L = d->lv[l];
         L.scale = (float)std::pow((double)scaleFactor, (double)l);
@@ -446,10 +501,18 @@ void orb_make_dims(int W, int H, int nfeatures, OrbDims* d) {
         L.w = (int)lrintf((float)W * L.inv);
         L.h = (int)lrintf((float)H * L.inv);
         L.off = off; L.row_off = rows;
+        L.mw = (L.w + 31) / 32; L.moff = mwords;
         off += (L.w * L.h + 15) / 16 * 16;
         rows += L.h;
+        mwords += L.mw * L.h;
     }
-    d->total_px = off; d->total_rows = rows;
+    d->total_px = off; d->total_rows = rows; d->total_mwords = mwords;
+    d->fast_tiles[0] = d->blur_tiles[0] = 0;
+    for (int l = 0; l < ORB_NLEVELS; l++) {
+        const OrbLevel& L = d->lv[l];
+        d->fast_tiles[l + 1] = d->fast_tiles[l] + ((L.w + kFastTX - 1) / kFastTX) * ((L.h + kFastTY - 1) / kFastTY);
+        d->blur_tiles[l + 1] = d->blur_tiles[l] + ((L.w + kBlurTX - 1) / kBlurTX) * ((L.h + kBlurTY - 1) / kBlurTY);
+    }
     float factor = (float)(1.0 / (double)scaleFactor);
     float nd = nfeatures * (1 - factor) / (1 - (float)std::pow((double)factor, (double)ORB_NLEVELS));
     int sum = 0;
@@ -466,7 +529,8 @@ void orb_make_dims(int W, int H, int nfeatures, OrbDims* d) {
 size_t orb_workspace_bytes(const OrbDims& d) {
     size_t b = 0;
     b += 4 * align_up((size_t)d.total_px + 64, 256);
-    b += 2 * align_up((size_t)d.total_rows * 4, 256);
+    b += align_up((size_t)d.total_rows * 4, 256);
+    b += align_up((size_t)d.total_mwords * 4, 256);
     b += align_up(32 * 4, 256);
     b += align_up((size_t)d.cand_cap * 4, 256) + align_up((size_t)d.cand_cap * 8, 256);
     b += align_up((size_t)d.kp_cap * 4, 256);
@@ -480,8 +544,8 @@ void orb_carve(const OrbDims& d, uint8_t* base, OrbWorkspace* ws) {
     ws->maskpyr = p; p += px;
     ws->score = p; p += px;
     ws->blur = p; p += px;
-    ws->row_count = (int32_t*)p; p += align_up((size_t)d.total_rows * 4, 256);
     ws->row_offset = (int32_t*)p; p += align_up((size_t)d.total_rows * 4, 256);
+    ws->candmask = (uint32_t*)p; p += align_up((size_t)d.total_mwords * 4, 256);
     ws->lvl_count = (int32_t*)p; p += align_up(32 * 4, 256);
     ws->cand_xy = (int32_t*)p; p += align_up((size_t)d.cand_cap * 4, 256);
     ws->cand_resp = (float*)p; p += align_up((size_t)d.cand_cap * 8, 256);
@@ -526,17 +590,11 @@ int orb_phase1_launch(const OrbDims& d, const OrbWorkspace* ws0, size_t ws_strid
         OVO_LAUNCH_CHECK();
     }
     {
-        dim3 grid(cdiv(d.W, kFastTX), cdiv(d.H, kFastTY), nb * ORB_NLEVELS);
-        OVO_LAUNCH(k_orb_fast, grid, dim3(kFastTX, kFastTY), 0, st, d, ws, ws_stride);
-        OVO_LAUNCH_CHECK();
-    }
-    {
-        dim3 grid(cdiv(d.H, 8), ORB_NLEVELS, nb);
-        OVO_LAUNCH(k_orb_nms<false>, grid, dim3(256), 0, st, d, ws, ws_stride, has_mask);
+        OVO_LAUNCH(k_orb_fast_nms, dim3(d.fast_tiles[ORB_NLEVELS], nb), dim3(256), 0, st, d, ws, ws_stride, has_mask);
         OVO_LAUNCH_CHECK();
         OVO_LAUNCH(k_orb_scan, dim3(nb), dim3(1024), 0, st, d, ws, ws_stride);
         OVO_LAUNCH_CHECK();
-        OVO_LAUNCH(k_orb_nms<true>, grid, dim3(256), 0, st, d, ws, ws_stride, has_mask);
+        OVO_LAUNCH(k_orb_emit, dim3(cdiv(d.total_rows, 8), nb), dim3(256), 0, st, d, ws, ws_stride);
         OVO_LAUNCH_CHECK();
     }
     {
@@ -545,8 +603,7 @@ int orb_phase1_launch(const OrbDims& d, const OrbWorkspace* ws0, size_t ws_strid
         OVO_LAUNCH_CHECK();
     }
     {
-        dim3 grid(cdiv(d.W, kBlurTX), cdiv(d.H, kBlurTY), nb * ORB_NLEVELS);
-        OVO_LAUNCH(k_orb_blur, grid, dim3(256), 0, st, d, ws, ws_stride);
+        OVO_LAUNCH(k_orb_blur, dim3(d.blur_tiles[ORB_NLEVELS], nb), dim3(256), 0, st, d, ws, ws_stride);
         OVO_LAUNCH_CHECK();
     }
     return 0;
