@@ -417,20 +417,32 @@ __global__ void __launch_bounds__(256) k_umeyama_b(PairBatch b, int cap) {
 }
 
 // ---- small glue -----------------------------------------------------------------------------------------------------------------
-__global__ void k_disp_post(const int16_t* __restrict__ disp, int W, int x0, int y0, int cw, int ch, float lo, float hi,
-                            float* __restrict__ out, uint8_t* __restrict__ mask, size_t in_stride, size_t out_stride) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
-    if (x >= cw) return;
-    const float d = __fdiv_rn((float)disp[in_stride * f + (size_t)(y + y0) * W + x + x0], 16.f);
-    out[out_stride * f + (size_t)y * cw + x] = d;
-    if (mask) mask[out_stride * f + (size_t)y * cw + x] = (d >= lo && d <= hi) ? 255 : 0;
+// 4 pixels per thread (CTA = 256 threads = 1024 consecutive output pixels): these kernels are bound by CTA dispatch otherwise
+__global__ void __launch_bounds__(256) k_disp_post(const int16_t* __restrict__ disp, int W, int x0, int y0, int cw, int ch, float lo,
+                                                   float hi, float* __restrict__ out, uint8_t* __restrict__ mask, size_t in_stride,
+                                                   size_t out_stride) {
+    const int f = blockIdx.y, n = cw * ch;
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        const int i = (blockIdx.x * 4 + e) * 256 + threadIdx.x;
+        if (i >= n) break;
+        const int y = i / cw, x = i - y * cw;
+        const float d = __fdiv_rn((float)disp[in_stride * f + (size_t)(y + y0) * W + x + x0], 16.f);
+        out[out_stride * f + i] = d;
+        if (mask) mask[out_stride * f + i] = (d >= lo && d <= hi) ? 255 : 0;
+    }
 }
 
-__global__ void k_crop_u8(const uint8_t* __restrict__ img, int pitch, size_t frame_stride, int x0, int y0, int cw, int ch,
-                          uint8_t* __restrict__ out) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
-    if (x >= cw) return;
-    out[((size_t)f * ch + y) * cw + x] = img[frame_stride * f + (size_t)(y + y0) * pitch + x + x0];
+__global__ void __launch_bounds__(256) k_crop_u8(const uint8_t* __restrict__ img, int pitch, size_t frame_stride, int x0, int y0, int cw,
+                                                 int ch, uint8_t* __restrict__ out) {
+    const int f = blockIdx.y, n = cw * ch;
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        const int i = (blockIdx.x * 4 + e) * 256 + threadIdx.x;
+        if (i >= n) break;
+        const int y = i / cw, x = i - y * cw;
+        out[(size_t)f * n + i] = img[frame_stride * f + (size_t)(y + y0) * pitch + x + x0];
+    }
 }
 
 // ---- rectification (SURVEY.md §8(f) n1 + n2) -----------------------------------------------------------------------------------
@@ -551,15 +563,15 @@ int reproject_launch(const float* disp, int pitch, int cw, int ch, int x0, int y
 
 int disp_post_launch(const int16_t* disp, int W, int H, int x0, int y0, int cw, int ch, float lo, float hi, float* disp_f32,
                      uint8_t* mask, int nb, cudaStream_t st) {
-    dim3 grid(cdiv(cw, 128), ch, nb);
-    OVO_LAUNCH(k_disp_post, grid, dim3(128), 0, st, disp, W, x0, y0, cw, ch, lo, hi, disp_f32, mask, (size_t)W * H, (size_t)cw * ch);
+    dim3 grid(cdiv(cw * ch, 1024), nb);
+    OVO_LAUNCH(k_disp_post, grid, dim3(256), 0, st, disp, W, x0, y0, cw, ch, lo, hi, disp_f32, mask, (size_t)W * H, (size_t)cw * ch);
     OVO_LAUNCH_CHECK();
     return 0;
 }
 
 int crop_launch(const uint8_t* img, int pitch, size_t frame_stride, int x0, int y0, int cw, int ch, int nb, uint8_t* out, cudaStream_t st) {
-    dim3 grid(cdiv(cw, 128), ch, nb);
-    OVO_LAUNCH(k_crop_u8, grid, dim3(128), 0, st, img, pitch, frame_stride, x0, y0, cw, ch, out);
+    dim3 grid(cdiv(cw * ch, 1024), nb);
+    OVO_LAUNCH(k_crop_u8, grid, dim3(256), 0, st, img, pitch, frame_stride, x0, y0, cw, ch, out);
     OVO_LAUNCH_CHECK();
     return 0;
 }

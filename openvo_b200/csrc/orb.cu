@@ -34,32 +34,43 @@ __device__ __forceinline__ T* fptr(T* p, size_t stride_bytes, int f) {
 
 // ---- pyramid ------------------------------------------------------------------------------------------------------
 // tab: per destination index (src index | c1 << 16), c1 = weight of src[index+1] in 1/256
-__global__ void k_orb_resize(OrbDims d, OrbWorkspace ws, size_t ws_stride, int level, const int32_t* __restrict__ xtab,
-                             const int32_t* __restrict__ ytab, int has_mask) {
+__global__ void __launch_bounds__(256) k_orb_resize(OrbDims d, OrbWorkspace ws, size_t ws_stride, int level,
+                                                    const int32_t* __restrict__ xtab, const int32_t* __restrict__ ytab, int has_mask) {
     const OrbLevel L = d.lv[level], S = d.lv[level - 1];
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
-    if (x >= L.w) return;
-    const int tx = xtab[x], ty = ytab[y];
-    const int i0 = tx & 0xFFFF, cx = tx >> 16, j0 = ty & 0xFFFF, cy = ty >> 16;
-    const int i1 = min(i0 + 1, S.w - 1), j1 = min(j0 + 1, S.h - 1);
-    for (int pl = 0; pl < 1 + has_mask; pl++) {
-        uint8_t* base = fptr(pl ? ws.maskpyr : ws.pyr, ws_stride, f);
-        const uint8_t* r0 = base + S.off + (size_t)j0 * S.w;
-        const uint8_t* r1 = base + S.off + (size_t)j1 * S.w;
-        const uint32_t h0 = r0[i0] * (256 - cx) + r0[i1] * cx;
-        const uint32_t h1 = r1[i0] * (256 - cx) + r1[i1] * cx;
-        uint32_t v = (h0 * (256 - cy) + h1 * cy + (1u << 15)) >> 16;
-        if (pl) v = v > 254 ? v : 0;  // THRESH_TOZERO(254) on the mask levels
-        base[L.off + (size_t)y * L.w + x] = (uint8_t)v;
+    const int f = blockIdx.y, n = L.w * L.h;
+#pragma unroll
+    for (int e = 0; e < 4; e++) {  // 4 pixels per thread: 1024 consecutive pixels per CTA
+        const int i = (blockIdx.x * 4 + e) * 256 + threadIdx.x;
+        if (i >= n) break;
+        const int y = i / L.w, x = i - y * L.w;
+        const int tx = xtab[x], ty = ytab[y];
+        const int i0 = tx & 0xFFFF, cx = tx >> 16, j0 = ty & 0xFFFF, cy = ty >> 16;
+        const int i1 = min(i0 + 1, S.w - 1), j1 = min(j0 + 1, S.h - 1);
+        for (int pl = 0; pl < 1 + has_mask; pl++) {
+            uint8_t* base = fptr(pl ? ws.maskpyr : ws.pyr, ws_stride, f);
+            const uint8_t* r0 = base + S.off + (size_t)j0 * S.w;
+            const uint8_t* r1 = base + S.off + (size_t)j1 * S.w;
+            const uint32_t h0 = r0[i0] * (256 - cx) + r0[i1] * cx;
+            const uint32_t h1 = r1[i0] * (256 - cx) + r1[i1] * cx;
+            uint32_t v = (h0 * (256 - cy) + h1 * cy + (1u << 15)) >> 16;
+            if (pl) v = v > 254 ? v : 0;  // THRESH_TOZERO(254) on the mask levels
+            base[L.off + i] = (uint8_t)v;
+        }
     }
 }
 
-__global__ void k_orb_copy_level0(OrbDims d, OrbWorkspace ws, size_t ws_stride, const uint8_t* __restrict__ img, int pitch,
-                                  size_t frame_stride, const uint8_t* __restrict__ mask, int mask_pitch, size_t mask_frame_stride) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
-    if (x >= d.W) return;
-    fptr(ws.pyr, ws_stride, f)[(size_t)y * d.W + x] = img[frame_stride * f + (size_t)y * pitch + x];
-    if (mask) fptr(ws.maskpyr, ws_stride, f)[(size_t)y * d.W + x] = mask[mask_frame_stride * f + (size_t)y * mask_pitch + x];
+__global__ void __launch_bounds__(256) k_orb_copy_level0(OrbDims d, OrbWorkspace ws, size_t ws_stride, const uint8_t* __restrict__ img,
+                                                         int pitch, size_t frame_stride, const uint8_t* __restrict__ mask, int mask_pitch,
+                                                         size_t mask_frame_stride) {
+    const int f = blockIdx.y, n = d.W * d.H;
+#pragma unroll
+    for (int e = 0; e < 4; e++) {  // 4 pixels per thread: 1024 consecutive pixels per CTA
+        const int i = (blockIdx.x * 4 + e) * 256 + threadIdx.x;
+        if (i >= n) break;
+        const int y = i / d.W, x = i - y * d.W;
+        fptr(ws.pyr, ws_stride, f)[i] = img[frame_stride * f + (size_t)y * pitch + x];
+        if (mask) fptr(ws.maskpyr, ws_stride, f)[i] = mask[mask_frame_stride * f + (size_t)y * mask_pitch + x];
+    }
 }
 
 // ---- FAST-9/16 score ----------------------------------------------------------------------------------------------------
@@ -580,13 +591,13 @@ int orb_phase1_launch(const OrbDims& d, const OrbWorkspace* ws0, size_t ws_strid
     const OrbWorkspace& ws = *ws0;
     const int has_mask = mask != nullptr;
     {
-        dim3 grid(cdiv(d.W, 128), d.H, nb);
-        OVO_LAUNCH(k_orb_copy_level0, grid, dim3(128), 0, st, d, ws, ws_stride, img, pitch, frame_stride, mask, mask_pitch, mask_frame_stride);
+        dim3 grid(cdiv(d.W * d.H, 1024), nb);
+        OVO_LAUNCH(k_orb_copy_level0, grid, dim3(256), 0, st, d, ws, ws_stride, img, pitch, frame_stride, mask, mask_pitch, mask_frame_stride);
         OVO_LAUNCH_CHECK();
     }
     for (int l = 1; l < ORB_NLEVELS; l++) {
-        dim3 grid(cdiv(d.lv[l].w, 128), d.lv[l].h, nb);
-        OVO_LAUNCH(k_orb_resize, grid, dim3(128), 0, st, d, ws, ws_stride, l, tab_dev + tab_off[2 * l], tab_dev + tab_off[2 * l + 1], has_mask);
+        dim3 grid(cdiv(d.lv[l].w * d.lv[l].h, 1024), nb);
+        OVO_LAUNCH(k_orb_resize, grid, dim3(256), 0, st, d, ws, ws_stride, l, tab_dev + tab_off[2 * l], tab_dev + tab_off[2 * l + 1], has_mask);
         OVO_LAUNCH_CHECK();
     }
     {

@@ -33,34 +33,39 @@ __device__ __forceinline__ T* frame_ptr(T* p, size_t stride_bytes, int f) {
 // ------------------------------------------------------------------------------------------------------------
 // A.4.1 row preparation.  One word per pixel and row type: byte0 = v, byte1 = min(vl, vr, v), byte2 = max(...).
 // ------------------------------------------------------------------------------------------------------------
-__global__ void k_sgbm_prep(const uint8_t* __restrict__ left, const uint8_t* __restrict__ right, int pitch,
-                            size_t frame_stride, SgbmDims d, SgbmWorkspace ws, size_t ws_stride) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y;
-    const int f = blockIdx.z >> 1, im = blockIdx.z & 1;
-    if (x >= d.W) return;
-    const int W = d.W, H = d.H, ftzero = d.ftzero;
+constexpr int kEPT = 4;  // pixels per thread of the small per-pixel kernels (CTA = 256 threads = 1024 consecutive pixels)
+
+__global__ void __launch_bounds__(256) k_sgbm_prep(const uint8_t* __restrict__ left, const uint8_t* __restrict__ right, int pitch,
+                                                   size_t frame_stride, SgbmDims d, SgbmWorkspace ws, size_t ws_stride) {
+    const int f = blockIdx.y >> 1, im = blockIdx.y & 1;
+    const int W = d.W, H = d.H, ftzero = d.ftzero, n = W * H;
     const uint8_t* I = (im ? right : left) + frame_stride * (size_t)f;
-    const uint8_t* r = I + (size_t)y * pitch;
-    const uint8_t* rn = I + (size_t)max(y - 1, 0) * pitch;
-    const uint8_t* rs = I + (size_t)min(y + 1, H - 1) * pitch;
-    uint2* out = reinterpret_cast<uint2*>(frame_ptr(ws.prep, ws_stride, f)) + (size_t)im * H * W;
-    auto G = [&](int xx) -> int {
-        if (xx <= 0 || xx >= W - 1) return ftzero;
-        int v = 2 * ((int)r[xx + 1] - (int)r[xx - 1]) + ((int)rn[xx + 1] - (int)rn[xx - 1]) + ((int)rs[xx + 1] - (int)rs[xx - 1]);
-        return min(max(v, -ftzero), ftzero) + ftzero;
-    };
-    auto R = [&](int xx) -> int { return (xx <= 0 || xx >= W - 1) ? ftzero : (int)r[xx]; };
-    uint2 o;
-    {
-        int c = G(x), vl = x > 0 ? (c + G(x - 1)) >> 1 : c, vr = x < W - 1 ? (c + G(x + 1)) >> 1 : c;
-        o.x = (uint32_t)c | ((uint32_t)min(min(vl, vr), c) << 8) | ((uint32_t)max(max(vl, vr), c) << 16);
+    uint2* out = reinterpret_cast<uint2*>(frame_ptr(ws.prep, ws_stride, f)) + (size_t)im * n;
+#pragma unroll
+    for (int e = 0; e < kEPT; e++) {
+        const int i = (blockIdx.x * kEPT + e) * 256 + threadIdx.x;
+        if (i >= n) break;
+        const int y = i / W, x = i - y * W;
+        const uint8_t* r = I + (size_t)y * pitch;
+        const uint8_t* rn = I + (size_t)max(y - 1, 0) * pitch;
+        const uint8_t* rs = I + (size_t)min(y + 1, H - 1) * pitch;
+        auto G = [&](int xx) -> int {
+            if (xx <= 0 || xx >= W - 1) return ftzero;
+            int v = 2 * ((int)r[xx + 1] - (int)r[xx - 1]) + ((int)rn[xx + 1] - (int)rn[xx - 1]) + ((int)rs[xx + 1] - (int)rs[xx - 1]);
+            return min(max(v, -ftzero), ftzero) + ftzero;
+        };
+        auto R = [&](int xx) -> int { return (xx <= 0 || xx >= W - 1) ? ftzero : (int)r[xx]; };
+        uint2 o;
+        {
+            int c = G(x), vl = x > 0 ? (c + G(x - 1)) >> 1 : c, vr = x < W - 1 ? (c + G(x + 1)) >> 1 : c;
+            o.x = (uint32_t)c | ((uint32_t)min(min(vl, vr), c) << 8) | ((uint32_t)max(max(vl, vr), c) << 16);
+        }
+        {
+            int c = R(x), vl = x > 0 ? (c + R(x - 1)) >> 1 : c, vr = x < W - 1 ? (c + R(x + 1)) >> 1 : c;
+            o.y = (uint32_t)c | ((uint32_t)min(min(vl, vr), c) << 8) | ((uint32_t)max(max(vl, vr), c) << 16);
+        }
+        out[i] = o;
     }
-    {
-        int c = R(x), vl = x > 0 ? (c + R(x - 1)) >> 1 : c, vr = x < W - 1 ? (c + R(x + 1)) >> 1 : c;
-        o.y = (uint32_t)c | ((uint32_t)min(min(vl, vr), c) << 8) | ((uint32_t)max(max(vl, vr), c) << 16);
-    }
-    out[(size_t)y * W + x] = o;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -716,24 +721,29 @@ __global__ void __launch_bounds__(64, NPR == 4 ? 6 : OVO_HOR_MINB) k_sgbm_horiz(
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void cswap(int& a, int& b) { const int t = min(a, b); b = max(a, b); a = t; }
 
-__global__ void k_median3(const int16_t* __restrict__ src, size_t src_stride, int16_t* __restrict__ dst, size_t dst_stride,
-                          int W, int H) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
-    if (x >= W) return;
+__global__ void __launch_bounds__(256) k_median3(const int16_t* __restrict__ src, size_t src_stride, int16_t* __restrict__ dst,
+                                                 size_t dst_stride, int W, int H) {
+    const int f = blockIdx.y, n = W * H;
     const int16_t* s = frame_ptr(src, src_stride, f);
     int16_t* o = frame_ptr(dst, dst_stride, f);
-    int v[9];
 #pragma unroll
-    for (int dy = -1; dy <= 1; dy++)
+    for (int e = 0; e < kEPT; e++) {
+        const int i = (blockIdx.x * kEPT + e) * 256 + threadIdx.x;
+        if (i >= n) break;
+        const int y = i / W, x = i - y * W;
+        int v[9];
 #pragma unroll
-        for (int dx = -1; dx <= 1; dx++)
-            v[(dy + 1) * 3 + dx + 1] = s[(size_t)min(max(y + dy, 0), H - 1) * W + min(max(x + dx, 0), W - 1)];
-    // 19-exchange median-of-9 network
-    cswap(v[1], v[2]); cswap(v[4], v[5]); cswap(v[7], v[8]); cswap(v[0], v[1]); cswap(v[3], v[4]); cswap(v[6], v[7]);
-    cswap(v[1], v[2]); cswap(v[4], v[5]); cswap(v[7], v[8]); cswap(v[0], v[3]); cswap(v[5], v[8]); cswap(v[4], v[7]);
-    cswap(v[3], v[6]); cswap(v[1], v[4]); cswap(v[2], v[5]); cswap(v[4], v[7]); cswap(v[4], v[2]); cswap(v[6], v[4]);
-    cswap(v[4], v[2]);
-    o[(size_t)y * W + x] = (int16_t)v[4];
+        for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+            for (int dx = -1; dx <= 1; dx++)
+                v[(dy + 1) * 3 + dx + 1] = s[(size_t)min(max(y + dy, 0), H - 1) * W + min(max(x + dx, 0), W - 1)];
+        // 19-exchange median-of-9 network
+        cswap(v[1], v[2]); cswap(v[4], v[5]); cswap(v[7], v[8]); cswap(v[0], v[1]); cswap(v[3], v[4]); cswap(v[6], v[7]);
+        cswap(v[1], v[2]); cswap(v[4], v[5]); cswap(v[7], v[8]); cswap(v[0], v[3]); cswap(v[5], v[8]); cswap(v[4], v[7]);
+        cswap(v[3], v[6]); cswap(v[1], v[4]); cswap(v[2], v[5]); cswap(v[4], v[7]); cswap(v[4], v[2]); cswap(v[6], v[4]);
+        cswap(v[4], v[2]);
+        o[i] = (int16_t)v[4];
+    }
 }
 
 __device__ __forceinline__ int ccl_find(volatile int32_t* L, int i) {
@@ -785,44 +795,57 @@ __global__ void __launch_bounds__(256) k_ccl_rows(const int16_t* __restrict__ im
         prev_last = __shfl_sync(0xffffffffu, v, 31);
     }
 }
-__global__ void k_ccl_vmerge(const int16_t* __restrict__ img, int32_t* label, int W, int H, int maxDiff, size_t img_stride,
-                             size_t ws_stride) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y + 1, f = blockIdx.z;
-    if (x >= W || y >= H) return;
+__global__ void __launch_bounds__(256) k_ccl_vmerge(const int16_t* __restrict__ img, int32_t* label, int W, int H, int maxDiff,
+                                                    size_t img_stride, size_t ws_stride) {
+    const int f = blockIdx.y, n = W * H;
     const int16_t* s = frame_ptr(img, img_stride, f);
-    const int i = y * W + x;
-    const int v = s[i], u = s[i - W];
-    if (v == kInv || u == kInv || abs(v - u) > maxDiff) return;
-    if (x > 0) {
-        const int vl = s[i - 1], ul = s[i - W - 1];
-        if (vl != kInv && ul != kInv && abs(v - vl) <= maxDiff && abs(u - ul) <= maxDiff && abs(vl - ul) <= maxDiff) return;
+#pragma unroll
+    for (int e = 0; e < kEPT; e++) {
+        const int i = W + (blockIdx.x * kEPT + e) * 256 + threadIdx.x;  // rows 1 .. H-1
+        if (i >= n) break;
+        const int x = i % W;
+        const int v = s[i], u = s[i - W];
+        if (v == kInv || u == kInv || abs(v - u) > maxDiff) continue;
+        if (x > 0) {
+            const int vl = s[i - 1], ul = s[i - W - 1];
+            if (vl != kInv && ul != kInv && abs(v - vl) <= maxDiff && abs(u - ul) <= maxDiff && abs(vl - ul) <= maxDiff) continue;
+        }
+        ccl_union(frame_ptr(label, ws_stride, f), i, i - W);
     }
-    ccl_union(frame_ptr(label, ws_stride, f), i, i - W);
 }
-__global__ void k_ccl_count(int32_t* label, int32_t* csize, int n, size_t ws_stride) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x, f = blockIdx.y;
+__global__ void __launch_bounds__(256) k_ccl_count(int32_t* label, int32_t* csize, int n, size_t ws_stride) {
+    const int f = blockIdx.y;
     int32_t* L = frame_ptr(label, ws_stride, f);
-    int r = -1;
-    if (i < n && L[i] >= 0) {
-        r = ccl_find(L, i);
-        L[i] = r;  // only ever lowers a label towards its root: concurrent finds stay valid
+#pragma unroll
+    for (int e = 0; e < kEPT; e++) {  // every thread runs all rounds: the warp votes below need the full warp
+        const int i = (blockIdx.x * kEPT + e) * 256 + threadIdx.x;
+        int r = -1;
+        if (i < n && L[i] >= 0) {
+            r = ccl_find(L, i);
+            L[i] = r;  // only ever lowers a label towards its root: concurrent finds stay valid
+        }
+        const uint32_t peers = __match_any_sync(0xffffffffu, r);
+        if (r >= 0 && (threadIdx.x & 31) == __ffs((int)peers) - 1) atomicAdd(&frame_ptr(csize, ws_stride, f)[r], __popc(peers));
     }
-    const uint32_t peers = __match_any_sync(0xffffffffu, r);
-    if (r >= 0 && (threadIdx.x & 31) == __ffs((int)peers) - 1) atomicAdd(&frame_ptr(csize, ws_stride, f)[r], __popc(peers));
 }
-__global__ void k_ccl_apply(const int16_t* __restrict__ img, const int32_t* __restrict__ label, const int32_t* __restrict__ csize,
-                            int16_t* __restrict__ out, int n, int maxSize, size_t img_stride, size_t ws_stride, size_t out_stride) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x, f = blockIdx.y;
-    if (i >= n) return;
-    const int16_t v = frame_ptr(img, img_stride, f)[i];
+__global__ void __launch_bounds__(256) k_ccl_apply(const int16_t* __restrict__ img, const int32_t* __restrict__ label,
+                                                   const int32_t* __restrict__ csize, int16_t* __restrict__ out, int n, int maxSize,
+                                                   size_t img_stride, size_t ws_stride, size_t out_stride) {
+    const int f = blockIdx.y;
     const int32_t* L = frame_ptr(label, ws_stride, f);
-    int16_t o = v;
-    if (v != kInv) {
-        int r = L[i];
-        while (L[r] != r) r = L[r];
-        if (frame_ptr(csize, ws_stride, f)[r] <= maxSize) o = (int16_t)kInv;
+#pragma unroll
+    for (int e = 0; e < kEPT; e++) {
+        const int i = (blockIdx.x * kEPT + e) * 256 + threadIdx.x;
+        if (i >= n) break;
+        const int16_t v = frame_ptr(img, img_stride, f)[i];
+        int16_t o = v;
+        if (v != kInv) {
+            int r = L[i];
+            while (L[r] != r) r = L[r];
+            if (frame_ptr(csize, ws_stride, f)[r] <= maxSize) o = (int16_t)kInv;
+        }
+        frame_ptr(out, out_stride, f)[i] = o;
     }
-    frame_ptr(out, out_stride, f)[i] = o;
 }
 
 template <int NPR, bool PAD>
@@ -888,8 +911,8 @@ int sgbm_launch(const SgbmDims& d, const SgbmWorkspace* ws0, size_t ws_stride, i
                 int pitch, size_t frame_stride, int16_t* disp_out, cudaStream_t st) {
     const SgbmWorkspace& ws = *ws0;
     {
-        dim3 grid(cdiv(d.W, 128), d.H, nb * 2);
-        OVO_LAUNCH(k_sgbm_prep, grid, dim3(128), 0, st, left, right, pitch, frame_stride, d, ws, ws_stride);
+        dim3 grid(cdiv(d.W * d.H, 256 * kEPT), nb * 2);
+        OVO_LAUNCH(k_sgbm_prep, grid, dim3(256), 0, st, left, right, pitch, frame_stride, d, ws, ws_stride);
         OVO_LAUNCH_CHECK();
     }
     int rc;
@@ -911,19 +934,19 @@ int sgbm_launch(const SgbmDims& d, const SgbmWorkspace* ws0, size_t ws_stride, i
     if (rc) return rc;
     const int n = d.W * d.H;
     const size_t out_stride = (size_t)n * 2;
-    dim3 gimg(cdiv(d.W, 128), d.H, nb);
+    dim3 gimg(cdiv(n, 256 * kEPT), nb);
     if (d.speckleWin <= 0) {
-        OVO_LAUNCH(k_median3, gimg, dim3(128), 0, st, ws.raw, ws_stride, disp_out, out_stride, d.W, d.H);
+        OVO_LAUNCH(k_median3, gimg, dim3(256), 0, st, ws.raw, ws_stride, disp_out, out_stride, d.W, d.H);
         OVO_LAUNCH_CHECK();
         return 0;
     }
-    OVO_LAUNCH(k_median3, gimg, dim3(128), 0, st, ws.raw, ws_stride, ws.med, ws_stride, d.W, d.H);
+    OVO_LAUNCH(k_median3, gimg, dim3(256), 0, st, ws.raw, ws_stride, ws.med, ws_stride, d.W, d.H);
     OVO_LAUNCH_CHECK();
-    dim3 glin(cdiv(n, 256), nb);
+    dim3 glin(cdiv(n, 256 * kEPT), nb);
     OVO_LAUNCH(k_ccl_rows, dim3(cdiv(d.H, 8), nb), dim3(256), 0, st, ws.med, ws.label, ws.csize, d.W, d.H, d.speckleDiff, ws_stride, ws_stride);
     OVO_LAUNCH_CHECK();
     if (d.H > 1) {
-        OVO_LAUNCH(k_ccl_vmerge, dim3(cdiv(d.W, 128), d.H - 1, nb), dim3(128), 0, st, ws.med, ws.label, d.W, d.H, d.speckleDiff, ws_stride, ws_stride);
+        OVO_LAUNCH(k_ccl_vmerge, dim3(cdiv(n - d.W, 256 * kEPT), nb), dim3(256), 0, st, ws.med, ws.label, d.W, d.H, d.speckleDiff, ws_stride, ws_stride);
         OVO_LAUNCH_CHECK();
     }
     OVO_LAUNCH(k_ccl_count, glin, dim3(256), 0, st, ws.label, ws.csize, n, ws_stride);
