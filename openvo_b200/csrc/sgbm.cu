@@ -89,7 +89,7 @@ __device__ __forceinline__ uint32_t bt_pair(uint32_t lw, uint32_t rw0, uint32_t 
 }
 
 // one row of a unit: horizontal sums of TX columns, folded into the vertical ring / running sums
-template <int SW2, int TX, bool EDGE>
+template <int SW2, int TX, bool EDGE, bool PAD>
 __device__ __forceinline__ void cost_row(const uint2* __restrict__ Lrow, const uint2* __restrict__ Rrow, int x0, int d0, int D, int W1,
                                          bool pad, uint32_t* slot, bool have_old, uint32_t (&vs)[TX]) {
     constexpr int BS = 2 * SW2 + 1;
@@ -101,12 +101,13 @@ __device__ __forceinline__ void cost_row(const uint2* __restrict__ Lrow, const u
     // the right-image word of disparity d+1 is the previous column's word of disparity d
     const uint2* Lb = Lrow + x0 + D;
     const uint2* Rb = Rrow + x0 + D - d0;
-    uint2 rprev = make_uint2(0, 0);
-    if (!EDGE && !pad) rprev = __ldg(Rb - SW2 - 1);
+    uint2 rw[2];  // right words of this and of the previous column, alternating so that no copy is needed
+    rw[0] = rw[1] = make_uint2(0, 0);
+    if (!EDGE && (!PAD || !pad)) rw[1] = __ldg(Rb - SW2 - 1);
 #pragma unroll
     for (int j = -SW2; j < TX + SW2; j++) {
         uint32_t pix = 0;
-        if (!pad) {
+        if (!PAD || !pad) {
             uint2 lw, r0, r1;
             if (EDGE) {
                 const int xx = min(max(x0 + j, 0), W1 - 1);
@@ -115,9 +116,9 @@ __device__ __forceinline__ void cost_row(const uint2* __restrict__ Lrow, const u
                 r1 = __ldg(Rrow + xx + D - d0 - 1);
             } else {
                 lw = __ldg(Lb + j);
-                r0 = __ldg(Rb + j);
-                r1 = rprev;
-                rprev = r0;
+                rw[(j + SW2) & 1] = __ldg(Rb + j);
+                r0 = rw[(j + SW2) & 1];
+                r1 = rw[((j + SW2) & 1) ^ 1];
             }
             const uint32_t cg = bt_pair(lw.x, r0.x, r1.x);
             const uint32_t cr = bt_pair(lw.y, r0.y, r1.y);
@@ -139,7 +140,7 @@ __device__ __forceinline__ void cost_row(const uint2* __restrict__ Lrow, const u
 #ifndef OVO_COST_MINB
 #define OVO_COST_MINB 5
 #endif
-template <int SW2, int TX>
+template <int SW2, int TX, bool PAD>
 __global__ void __launch_bounds__(kCostThreads, OVO_COST_MINB) k_sgbm_cost(SgbmDims d, SgbmWorkspace ws, size_t ws_stride) {
     constexpr int BS = 2 * SW2 + 1;
     __shared__ uint32_t ring[BS * TX * kCostThreads];
@@ -169,8 +170,8 @@ __global__ void __launch_bounds__(kCostThreads, OVO_COST_MINB) k_sgbm_cost(SgbmD
         const uint2* Lrow = prep + (size_t)yc * W;
         const uint2* Rrow = Lrow + plane;
         uint32_t* slot = ring + (size_t)(k % BS) * TX * kCostThreads + tid;
-        if (edge) cost_row<SW2, TX, true>(Lrow, Rrow, x0, d0, D, W1, pad, slot, k >= BS, vs);
-        else cost_row<SW2, TX, false>(Lrow, Rrow, x0, d0, D, W1, pad, slot, k >= BS, vs);
+        if (edge) cost_row<SW2, TX, true, PAD>(Lrow, Rrow, x0, d0, D, W1, pad, slot, k >= BS, vs);
+        else cost_row<SW2, TX, false, PAD>(Lrow, Rrow, x0, d0, D, W1, pad, slot, k >= BS, vs);
         const int y = r - SW2;
         if (y >= y0) {
             uint32_t* out = Cw + ((size_t)y * W1 + x0) * npairs + threadIdx.x;
@@ -873,7 +874,8 @@ int launch_cost(const SgbmDims& d, const SgbmWorkspace& ws, size_t ws_stride, in
     const int npairs = d.Dp / 2, upb = kCostThreads / npairs;
     const int units = cdiv(d.W1, TX) * cdiv(d.H, kCostRS);
     dim3 grid(cdiv(units, upb), 1, nb), block(npairs, upb);
-    { auto k_sgbm_cost_t = k_sgbm_cost<SW2, TX>; OVO_LAUNCH(k_sgbm_cost_t, grid, block, 0, st, d, ws, ws_stride); }
+    if (d.D == d.Dp) { auto k_sgbm_cost_t = k_sgbm_cost<SW2, TX, false>; OVO_LAUNCH(k_sgbm_cost_t, grid, block, 0, st, d, ws, ws_stride); }
+    else { auto k_sgbm_cost_t = k_sgbm_cost<SW2, TX, true>; OVO_LAUNCH(k_sgbm_cost_t, grid, block, 0, st, d, ws, ws_stride); }
     OVO_LAUNCH_CHECK();
     return 0;
 }
