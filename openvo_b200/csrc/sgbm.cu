@@ -380,13 +380,10 @@ __global__ void __launch_bounds__(256) k_sgbm_vert(SgbmDims d, SgbmWorkspace ws,
 // order-independent: min cost, ties to the larger x (= larger d), which is what the reference's right-to-left sweep keeps.
 // ------------------------------------------------------------------------------------------------------------
 #ifndef OVO_HOR_MINB
-#define OVO_HOR_MINB 10
-#endif
-#ifndef OVO_HOR_K
-#define OVO_HOR_K 4
+#define OVO_HOR_MINB 8
 #endif
 template <int NPR>
-__host__ __device__ constexpr int horiz_seg() { return NPR == 4 ? 4 : OVO_HOR_K; }  // K: cells per checkpoint segment
+__host__ __device__ constexpr int horiz_seg() { return 4; }  // K: cells per checkpoint segment (= cells per batched selection)
 
 template <int NPR>
 __device__ __forceinline__ uint32_t half_of(const uint32_t (&S)[NPR], int k) {  // k = 2*r + h, compile-time after unrolling
@@ -443,6 +440,53 @@ __device__ __forceinline__ void wta_cell(const uint32_t (&S)[NPR], int lane, con
     }
 }
 
+// Selection for the K = 4 cells of a segment at once (uniquenessRatio < 100, the usual case).  The warp has parked the
+// four S vectors in shared memory; 8 lanes share a cell, each scanning Dp/8 consecutive disparities, so the reductions,
+// the neighbour look-ups and the stores are paid once per four cells.  Padded disparities hold MAX_COST and the larger
+// d, so they can neither win the argmin nor lower the runner-up.
+template <int NPR>
+__device__ __forceinline__ void wta_batch(const uint32_t* svec, int lane, const SgbmDims& d, int xo, int dirx, int cnt, uint32_t* selA,
+                                          uint32_t* selB, uint16_t* selBest) {
+    constexpr int WPC = 32 * NPR, NW = 4 * NPR;  // words per cell, words per lane
+    const int g = lane >> 3, q = lane & 7;
+    uint32_t w[NW];
+#pragma unroll
+    for (int i = 0; i < NW; i += 4) {
+        const uint4 t = *reinterpret_cast<const uint4*>(svec + g * WPC + q * NW + i);
+        w[i] = t.x; w[i + 1] = t.y; w[i + 2] = t.z; w[i + 3] = t.w;
+    }
+    // first d minimising S: the smallest (S << 9 | d)
+    uint32_t kbest = 0xFFFFFFFFu;
+#pragma unroll
+    for (int i = 0; i < NW; i++) {
+        kbest = min(kbest, (w[i] & 0xFFFFu) * 512u + (uint32_t)(2 * i));
+        kbest = min(kbest, (w[i] >> 16) * 512u + (uint32_t)(2 * i + 1));
+    }
+    kbest += (uint32_t)(q * 2 * NW);
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) kbest = min(kbest, __shfl_xor_sync(0xffffffffu, kbest, o));
+    const int minS = (int)(kbest >> 9), best = (int)(kbest & 511u);
+    // runner-up over |d - best| > 1: bit c of `near` marks this lane's c-th disparity as one of best-1, best, best+1
+    const uint32_t sh = (uint32_t)(best - q * 2 * NW + 1);  // position of best+1's successor bit; huge when out of range
+    const uint32_t near = sh < 32u ? ((7u << sh) >> 2) : 0u;
+    uint32_t m2 = 0xFFFFu;
+#pragma unroll
+    for (int i = 0; i < NW; i++) {
+        if (!(near & (1u << (2 * i)))) m2 = min(m2, w[i] & 0xFFFFu);
+        if (!(near & (1u << (2 * i + 1)))) m2 = min(m2, w[i] >> 16);
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) m2 = min(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+    if (q == 0 && g < cnt) {
+        const uint16_t* sh16 = reinterpret_cast<const uint16_t*>(svec + g * WPC);
+        const uint32_t sm1 = sh16[max(best - 1, 0)], sp1 = sh16[min(best + 1, 2 * WPC - 1)];  // only used when 0 < best < D-1
+        const int x1 = xo - dirx * g;
+        selA[x1] = (uint32_t)minS | (m2 << 16);
+        selB[x1] = sm1 | (sp1 << 16);
+        selBest[x1] = (uint16_t)best;
+    }
+}
+
 template <int NPR>
 struct HorizRow {          // per-thread view of one row
     const uint32_t* C;     // + row offset + lane
@@ -453,6 +497,7 @@ struct HorizRow {          // per-thread view of one row
     int xa, n1, n2;        // first cell and length of the own phase-1 sweep; length of the other warp's
     uint32_t *selA, *selB;
     uint16_t* selBest;
+    uint32_t* svec;        // this warp's shared-memory slots for the K cost vectors of a segment
 };
 
 #ifndef OVO_HOR_PF1
@@ -523,13 +568,14 @@ __device__ __forceinline__ void horiz_load_lv(const HorizRow<NPR>& R, ptrdiff_t 
 // One K-cell segment of phase 2.  On entry cb / ckv / lv hold C, the other warp's checkpoint and Lv[0..2] of segment j
 // (requested one segment earlier); on exit they hold those of segment j-1.  FULL: all K cells exist (only the segment
 // next to the rendezvous can be short).
-template <int NPR, bool PAD, bool HH, int DIRX, bool FULL>
+template <int NPR, bool PAD, bool HH, bool BATCH, int DIRX, bool FULL>
 __device__ __forceinline__ void horiz_segment(const SgbmDims& d, const HorizRow<NPR>& R, PathState<NPR>& s, int lane, int j, int cnt,
                                               uint32_t (&cb)[horiz_seg<NPR>()][NPR], uint32_t (&ckv)[NPR],
                                               uint32_t (&lv)[3][horiz_seg<NPR>()][NPR], const uint32_t (&padmask)[NPR],
                                               uint32_t P1P1, uint32_t P2) {
     constexpr int WPC = 32 * NPR, K = horiz_seg<NPR>(), DS = DIRX * WPC;
     const bool lane_first = lane == 0, lane_last = lane == 31;
+    constexpr bool batched = BATCH;  // selection of the K cells at once; the odd uniquenessRatio >= 100 goes cell by cell
     // the other warp's cell k (counted along ITS sweep) sits at x = xo - DIRX * k
     const int xo = (DIRX > 0 ? d.W1 - 1 : 0) - DIRX * (j * K);
     const ptrdiff_t o0 = (ptrdiff_t)xo * WPC;  // cell i of the segment is at o0 - i * DS
@@ -595,8 +641,14 @@ __device__ __forceinline__ void horiz_segment(const SgbmDims& d, const HorizRow<
             uint32_t S[NPR];
 #pragma unroll
             for (int r = 0; r < NPR; r++) S[r] = __viaddmin_u16x2(sv[i][r], s.L[r], kMaxC2);
-            wta_cell<NPR, PAD>(S, lane, d, xo - DIRX * i, R.selA, R.selB, R.selBest);
+            if (batched) stv<NPR>(R.svec + i * WPC + lane * NPR, S);
+            else wta_cell<NPR, PAD>(S, lane, d, xo - DIRX * i, R.selA, R.selB, R.selBest);
         }
+    }
+    if (batched) {
+        __syncwarp();
+        wta_batch<NPR>(R.svec, lane, d, xo, DIRX, FULL ? K : cnt, R.selA, R.selB, R.selBest);
+        __syncwarp();
     }
     if (j > 0) {
 #pragma unroll
@@ -608,7 +660,7 @@ __device__ __forceinline__ void horiz_segment(const SgbmDims& d, const HorizRow<
     }
 }
 
-template <int NPR, bool PAD, bool HH, int DIRX>
+template <int NPR, bool PAD, bool HH, bool BATCH, int DIRX>
 __device__ __forceinline__ void horiz_phase2(const SgbmDims& d, const HorizRow<NPR>& R, PathState<NPR>& s, int lane) {
     constexpr int WPC = 32 * NPR, K = horiz_seg<NPR>(), DS = DIRX * WPC;
     const int n2 = R.n2;
@@ -630,13 +682,13 @@ __device__ __forceinline__ void horiz_phase2(const SgbmDims& d, const HorizRow<N
         horiz_load_lv<NPR, DIRX, false>(R, o0, cnt, lv);
     }
     if (cnt < K) {
-        horiz_segment<NPR, PAD, HH, DIRX, false>(d, R, s, lane, j, cnt, cb, ckv, lv, padmask, P1P1, P2);
+        horiz_segment<NPR, PAD, HH, BATCH, DIRX, false>(d, R, s, lane, j, cnt, cb, ckv, lv, padmask, P1P1, P2);
         j--;
     }
-    for (; j >= 0; j--) horiz_segment<NPR, PAD, HH, DIRX, true>(d, R, s, lane, j, K, cb, ckv, lv, padmask, P1P1, P2);
+    for (; j >= 0; j--) horiz_segment<NPR, PAD, HH, BATCH, DIRX, true>(d, R, s, lane, j, K, cb, ckv, lv, padmask, P1P1, P2);
 }
 
-template <int NPR, bool PAD, bool HH>
+template <int NPR, bool PAD, bool HH, bool BATCH>
 __global__ void __launch_bounds__(64, NPR == 4 ? 6 : OVO_HOR_MINB) k_sgbm_horiz(SgbmDims d, SgbmWorkspace ws, size_t ws_stride) {
     OVO_DYN_SMEM(uint32_t, hsm);
     uint32_t* d2key = hsm;                                        // [W]
@@ -648,6 +700,7 @@ __global__ void __launch_bounds__(64, NPR == 4 ? 6 : OVO_HOR_MINB) k_sgbm_horiz(
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int W = d.W, W1 = d.W1, H = d.H;
     constexpr int WPC = 32 * NPR, K = horiz_seg<NPR>();
+    __shared__ __align__(16) uint32_t svec_s[2][K * WPC];
     for (int i = threadIdx.x; i < W; i += blockDim.x) {
         d2key[i] = kD2Init;
         disp1s[i] = (int16_t)kInv;
@@ -668,14 +721,15 @@ __global__ void __launch_bounds__(64, NPR == 4 ? 6 : OVO_HOR_MINB) k_sgbm_horiz(
     R.n1 = wid == 0 ? mid : W1 - mid;
     R.n2 = W1 - R.n1;
     R.selA = selA; R.selB = selB; R.selBest = selBest;
+    R.svec = svec_s[wid];
 
     PathState<NPR> s;
     path_reset<NPR>(s);
     if (wid == 0) horiz_phase1<NPR, PAD, 1>(d, R, s, lane);
     else horiz_phase1<NPR, PAD, -1>(d, R, s, lane);
     __syncthreads();
-    if (wid == 0) horiz_phase2<NPR, PAD, HH, 1>(d, R, s, lane);
-    else horiz_phase2<NPR, PAD, HH, -1>(d, R, s, lane);
+    if (wid == 0) horiz_phase2<NPR, PAD, HH, BATCH, 1>(d, R, s, lane);
+    else horiz_phase2<NPR, PAD, HH, BATCH, -1>(d, R, s, lane);
     __syncthreads();
     // ---- uniqueness, sub-pixel refinement and disp2 (A.4.4), data-parallel over the row
     {
@@ -856,15 +910,15 @@ int launch_paths(const SgbmDims& d, const SgbmWorkspace& ws, size_t ws_stride, i
     OVO_LAUNCH_CHECK();
     dim3 gh(d.H, nb);
     const size_t smem = (size_t)d.W * 6 + (size_t)d.W1 * 10 + 16;
-    if (d.mode) {
-        auto k_sgbm_horiz_t = k_sgbm_horiz<NPR, PAD, true>;
-        if (smem > 48 * 1024) OVO_CUDA(cudaFuncSetAttribute(k_sgbm_horiz_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto go = [&](auto k_sgbm_horiz_t) -> int {
+        if (smem > 40 * 1024) OVO_CUDA(cudaFuncSetAttribute(k_sgbm_horiz_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         OVO_LAUNCH(k_sgbm_horiz_t, gh, dim3(64), smem, st, d, ws, ws_stride);
-    } else {
-        auto k_sgbm_horiz_t = k_sgbm_horiz<NPR, PAD, false>;
-        if (smem > 48 * 1024) OVO_CUDA(cudaFuncSetAttribute(k_sgbm_horiz_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        OVO_LAUNCH(k_sgbm_horiz_t, gh, dim3(64), smem, st, d, ws, ws_stride);
-    }
+        return 0;
+    };
+    int rc;
+    if (d.uniq < 100) rc = d.mode ? go(k_sgbm_horiz<NPR, PAD, true, true>) : go(k_sgbm_horiz<NPR, PAD, false, true>);
+    else rc = d.mode ? go(k_sgbm_horiz<NPR, PAD, true, false>) : go(k_sgbm_horiz<NPR, PAD, false, false>);
+    if (rc) return rc;
     OVO_LAUNCH_CHECK();
     return 0;
 }
