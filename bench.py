@@ -25,10 +25,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CONFIGS = {
-    "K": dict(W=1241, H=376, D=128, n=2000, name="KITTI-shaped 1241x376 stereo, ORB 2000 kp, StereoSGBM 128 disp"),
-    "F": dict(W=1920, H=1080, D=256, n=5000, name="1920x1080 stereo, ORB 5000 kp, StereoSGBM 256 disp"),
-    "U": dict(W=3840, H=2160, D=256, n=10000, name="3840x2160 stereo, ORB 10000 kp, StereoSGBM 256 disp"),
-    "S": dict(W=640, H=200, D=64, n=500, name="small 640x200 stereo, ORB 500 kp, StereoSGBM 64 disp (dev only)"),
+    "K": dict(W=1241, H=376, D=128, n=2000, seqs=48, name="KITTI-shaped 1241x376 stereo, ORB 2000 kp, StereoSGBM 128 disp"),
+    "F": dict(W=1920, H=1080, D=256, n=5000, seqs=8, name="1920x1080 stereo, ORB 5000 kp, StereoSGBM 256 disp"),
+    "U": dict(W=3840, H=2160, D=256, n=10000, seqs=2, name="3840x2160 stereo, ORB 10000 kp, StereoSGBM 256 disp"),
+    "S": dict(W=640, H=200, D=64, n=500, seqs=48, name="small 640x200 stereo, ORB 500 kp, StereoSGBM 64 disp (dev only)"),
 }
 N_DISTINCT = 6  # distinct rendered frames; sequences ping-pong through them with different phases
 
@@ -171,8 +171,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="K", choices=list(CONFIGS))
-    ap.add_argument("--seqs", type=int, default=24, help="independent sequences (= frames per step) per GPU")
-    ap.add_argument("--threads", type=int, default=3, help="host threads (each with its own CUDA stream and share of the sequences)")
+    ap.add_argument("--seqs", type=int, default=0, help="independent sequences (= frames per step) per GPU; 0 = the config's default "
+                                                        "(48 at the KITTI shape: two batches of 24 in flight)")
+    ap.add_argument("--select-threads", type=int, default=0,
+                    help="host threads per batch for the keypoint-selection step (OVO_SELECT_THREADS); 0 = min(8, cores / ranks)")
+    ap.add_argument("--threads", type=int, default=1, help="host threads (each drives --groups batches round-robin)")
+    ap.add_argument("--groups", type=int, default=2,
+                    help="batches in flight per host thread: each has its own CUDA stream / workspace and a share of the sequences; the "
+                         "thread finishes batch g of step s, queues batch g of step s+1 and moves on to g+1, so the host-side "
+                         "keypoint selection of one batch overlaps device work of the others")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--_cpu_worker", nargs=5, default=None)
     a = ap.parse_args()
@@ -213,6 +220,8 @@ def main():
                         "sample": "oracle port on cv2 (the reference's CPU path): %d processes x %d frames (cv2 threads=1 each), "
                                   "wall %.1f s" % (cores, nfr, wall)}
 
+    if "OVO_SELECT_THREADS" not in os.environ:
+        os.environ["OVO_SELECT_THREADS"] = str(a.select_threads or max(2, min(8, host_cores() // max(1, world))))
     import torch
     import torch.distributed as dist
     from openvo_b200 import StereoCamera, synth, _native
@@ -221,7 +230,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
-    S = a.seqs
+    S = a.seqs or cfg["seqs"]
     cam = StereoCamera(**synth.camera_args(cfg["W"], cfg["H"], cfg["D"]))
 
     def barrier():
@@ -230,41 +239,50 @@ def main():
         torch.cuda.synchronize()
 
     NT = max(1, min(a.threads, S))
-    assert S % NT == 0, "--seqs must be divisible by --threads"
-    SP = S // NT  # sequences per host thread
-    streams = [torch.cuda.Stream() for _ in range(NT)]
+    NG = max(1, min(a.groups, S // NT))
+    assert S % (NT * NG) == 0, "--seqs must be divisible by --threads x --groups"
+    SP = S // (NT * NG)  # sequences per batch
+    streams = [[torch.cuda.Stream() for _ in range(NG)] for _ in range(NT)]
 
     def fresh():
-        return [BatchOdometer(cam, SP, nfeatures=cfg["n"], engine_tag=t, preprocessed_frames=True) for t in range(NT)]
+        return [[BatchOdometer(cam, SP, nfeatures=cfg["n"], engine_tag=t * NG + g, preprocessed_frames=True) for g in range(NG)]
+                for t in range(NT)]
 
     dev_L, dev_R = torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()
     pin_L = [torch.from_numpy(L[i]).pin_memory() for i in range(len(L))]   # e2e inputs: host frames in pinned memory
     pin_R = [torch.from_numpy(R[i]).pin_memory() for i in range(len(R))]
     lib = _native.load()
 
-    def run_part(bo, t, steps, first_step, host):
+    def begin(bo, t, g, s, host):
+        idx = [frame_index(s, rank * S + (t * NG + g) * SP + q) for q in range(SP)]
+        if host:
+            bo.begin([pin_L[i] for i in idx], [pin_R[i] for i in idx])  # one pinned host frame per sequence, H2D every step
+        else:
+            ti = torch.tensor(idx, device="cuda")
+            bo.begin_device(dev_L[ti], dev_R[ti])
+
+    def run_part(bos_t, t, steps, first_step, host):
+        """One host thread, NG batches round-robin: finish batch g of step s, queue batch g of step s+1, go on to batch g+1."""
         ok = 0
+        for g in range(NG):
+            with torch.cuda.stream(streams[t][g]):
+                begin(bos_t[g], t, g, first_step, host)
         for s in range(first_step, first_step + steps):
-            idx = [frame_index(s, rank * S + t * SP + q) for q in range(SP)]
-            if host:
-                res = bo.update([pin_L[i] for i in idx], [pin_R[i] for i in idx])  # one pinned host frame per sequence, H2D every step
-            else:
-                ti = torch.tensor(idx, device="cuda")
-                res = bo.update_device(dev_L[ti], dev_R[ti])
-            ok += sum(res)
+            for g in range(NG):
+                with torch.cuda.stream(streams[t][g]):
+                    ok += sum(bos_t[g].finish())
+                    if s + 1 < first_step + steps:
+                        begin(bos_t[g], t, g, s + 1, host)
         return ok
 
     def run(bos, steps, first_step, host):
-        """Every host thread drives its share of the sequences on its own stream; host-side work of one (keypoint selection,
-        launches) overlaps device work of the other."""
         oks, errs = [0] * NT, []
         torch.cuda.synchronize()
 
         def work(t):
             try:
                 torch.cuda.set_device(local_rank)
-                with torch.cuda.stream(streams[t]):
-                    oks[t] = run_part(bos[t], t, steps, first_step, host)
+                oks[t] = run_part(bos[t], t, steps, first_step, host)
             except Exception as e:  # pragma: no cover
                 errs.append(e)
         if NT == 1:
@@ -277,14 +295,15 @@ def main():
                 x.join()
         if errs:
             raise errs[0]
-        for st in streams:
-            torch.cuda.current_stream().wait_stream(st)
+        for sl in streams:
+            for st in sl:
+                torch.cuda.current_stream().wait_stream(st)
         return sum(oks)
 
     def timed(host):
         bos = fresh()
         run(bos, warmup, 0, host)
-        engs = [b.engine for b in bos]
+        engs = [b.engine for bt in bos for b in bt]
         h2d0, d2h0, l0 = sum(e.h2d_bytes for e in engs), sum(e.d2h_bytes for e in engs), lib.ovo_launch_count()
         sampler = ClockSampler(local_rank)
         barrier()
@@ -293,7 +312,7 @@ def main():
         e0.record()
         ok = run(bos, a.steps, warmup, host)
         if world > 1:  # the only exchange: per-frame relative transforms + status, once per chunk
-            ods = [od for b in bos for od in b.odometers]
+            ods = [od for bt in bos for b in bt for od in b.odometers]
             T = np.stack([od.last_T if od.last_T is not None else np.eye(4) for od in ods])[:, None]
             st = np.ones((S, 1), np.int32)
             odist.gather_poses(T, st, odist.shard_sequences(S * world, rank, world), S * world)
@@ -319,8 +338,11 @@ def main():
     if rank == 0:
         bos = dev["bos"]
         lib.ovo_profile_enable(1)
-        with torch.cuda.stream(streams[0]):  # one stream only: event pairs around each launch must not see the other stream's kernels
-            run_part(bos[0], 0, min(a.steps, 5), warmup + a.steps, False)
+        b0 = bos[0][0]
+        with torch.cuda.stream(streams[0][0]):  # one stream only: event pairs around each launch must not see another stream's kernels
+            for s_ in range(warmup + a.steps, warmup + a.steps + min(a.steps, 5)):
+                begin(b0, 0, 0, s_, False)
+                b0.finish()
         torch.cuda.synchronize()
         prof = _native.profile_read(lib)
         lib.ovo_profile_enable(0)
@@ -333,7 +355,7 @@ def main():
         except Exception:
             pass
         peak, which = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
-        abytes = algorithmic_bytes(top, bos[0].engine, SP)
+        abytes = algorithmic_bytes(top, b0.engine, SP)
         dur_s = prof[top][0] / prof[top][1] * 1e-3
         achieved = abytes / dur_s / 1e9 if dur_s > 0 else 0.0
         traffic = None
@@ -350,8 +372,8 @@ def main():
         def t_of(prefixes):
             return sum(v["ms_per_launch"] * v["launches"] for k, v in per_kernel.items() if k.startswith(prefixes)) / (min(a.steps, 5) * SP)
         W_, H_, D_ = cfg["W"], cfg["H"], cfg["D"]
-        eng0 = dev["bos"][0].engine
-        nkp = float(np.mean([od._cur.n_kp for b in dev["bos"] for od in b.odometers if od._cur is not None] or [0]))
+        eng0 = dev["bos"][0][0].engine
+        nkp = float(np.mean([od._cur.n_kp for bt in dev["bos"] for b in bt for od in b.odometers if od._cur is not None] or [0]))
         ipk = {}
         try:
             ipk = json.load(open(os.path.join(ROOT, "profiles", "int_peaks.json")))
@@ -382,7 +404,8 @@ def main():
         line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": a.steps, "warmup": warmup,
                 "ms_per_step": dev["ms"] / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i16",
                 "data": "synthetic",
-                "config": {"workload": workload, "frames_per_step": S * world, "sequences_per_gpu": S, "host_threads": NT, "distinct_frames": N_DISTINCT,
+                "config": {"workload": workload, "frames_per_step": S * world, "sequences_per_gpu": S, "host_threads": NT, "batches_in_flight_per_thread": NG,
+                           "sequences_per_batch": SP, "distinct_frames": N_DISTINCT,
                            "l2_policy": "inputs+working set larger than L2: %d frames x ~0.55 GB SGBM volumes per step" % S,
                            "frames_committed": dev["ok"]},
                 "clocks": dev["clocks"], "gpu_launches": dev["launches"],

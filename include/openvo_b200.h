@@ -94,6 +94,11 @@ int ovo_reproject_3d(ovo_ctx* ctx, const float* disp_f32_dev, float* xyz_dev, vo
  * reproduced on the host between the two device phases (see DESIGN.md "retainBest"). */
 int ovo_orb_detect_compute(ovo_ctx* ctx, const uint8_t* img_dev, const uint8_t* mask_dev, int nb, float* kp_dev,
                            uint8_t* desc_dev, int* n_kp_host, void* stream);
+/* The same call in two halves, for drivers that keep several batches in flight from one host thread: `begin` only queues
+ * the detection phase on `stream` (asynchronous); `finish` waits for it, runs the host-side retainBest and queues the
+ * descriptor phase.  begin + finish on the same ctx / stream == ovo_orb_detect_compute. */
+int ovo_orb_detect_begin(ovo_ctx* ctx, const uint8_t* img_dev, const uint8_t* mask_dev, int nb, void* stream);
+int ovo_orb_detect_finish(ovo_ctx* ctx, int nb, float* kp_dev, uint8_t* desc_dev, int* n_kp_host, void* stream);
 
 /* Seam S-E — replaces matcher.knnMatch(desc1, desc2, k=2) (ref: src/openVO/stereo_odometer.py:163).
  * nn: i32 [nq][4] = (trainIdx0, dist0, trainIdx1, dist1); ties resolve to the lowest train index. */

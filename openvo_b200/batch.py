@@ -14,6 +14,7 @@ class BatchOdometer:
         self.stereo = stereo_camera
         self.odometers = [StereoOdometer(stereo_camera, nfeatures=nfeatures, _max_batch=self.n, _engine_tag=engine_tag, **kw) for _ in range(self.n)]
         self.engine = self.odometers[0]._engine()
+        self._pending = None
 
     def update(self, lefts, rights):
         """lefts/rights: numpy uint8 host frames [S,H,W] (gray) or [S,H,W,3] (BGR); rectified on the device unless the
@@ -24,8 +25,25 @@ class BatchOdometer:
 
     def update_device(self, lefts, rights):
         """Same, with the frames already resident on the device (torch uint8 [S,H,W])."""
+        self.begin_device(lefts, rights)
+        return self.finish()
+
+    # update() in two halves, so that one host thread can keep several BatchOdometers (each on its own CUDA stream) busy:
+    # begin() only queues device work for the next frames; finish() waits for it, selects keypoints on the host, runs the
+    # pair step and advances the S state machines.  begin + finish == update.
+    def begin(self, lefts, rights):
         eng = self.engine
-        frames = eng.frames(lefts, rights)
+        l, r = self.stereo._prepare_device(eng, lefts, rights, self.odometers[0].preprocessed_frames, key="b")
+        self.begin_device(l, r)
+
+    def begin_device(self, lefts, rights):
+        assert self._pending is None, "finish() the previous batch first"
+        self._pending = self.engine.frames_begin(lefts, rights)
+
+    def finish(self):
+        eng = self.engine
+        token, self._pending = self._pending, None
+        frames = eng.frames_finish(token)
         queued, jobs = [], []
         for i, (od, fr) in enumerate(zip(self.odometers, frames)):
             if od._cur is not None and fr.n_kp >= od.min_matches and fr.n_kp >= 2:

@@ -302,14 +302,24 @@ int ovo_reproject_3d(ovo_ctx* c, const float* disp_f32, float* xyz, void* stream
     return reproject_launch(disp_f32, c->L.cw, c->L.cw, c->L.ch, c->L.x0, c->L.y0, c->cfg.Q, xyz, (cudaStream_t)stream);
 }
 
+int ovo_orb_detect_begin(ovo_ctx* c, const uint8_t* img, const uint8_t* mask, int nb, void* stream) {
+    CHECK_CTX(c, nb);
+    const Layout& L = c->L;
+    const size_t fs = (size_t)L.cw * L.ch;
+    return orb_phase1_launch(L.orb, &c->orb0, L.frame_bytes, c->tab_dev, L.tab_off, nb, img, L.cw, fs, mask, L.cw, fs, (cudaStream_t)stream);
+}
+
 int ovo_orb_detect_compute(ovo_ctx* c, const uint8_t* img, const uint8_t* mask, int nb, float* kp, uint8_t* desc, int* n_kp_host,
                            void* stream) {
+    if (ovo_orb_detect_begin(c, img, mask, nb, stream)) return 1;
+    return ovo_orb_detect_finish(c, nb, kp, desc, n_kp_host, stream);
+}
+
+int ovo_orb_detect_finish(ovo_ctx* c, int nb, float* kp, uint8_t* desc, int* n_kp_host, void* stream) {
     CHECK_CTX(c, nb);
     cudaStream_t st = (cudaStream_t)stream;
     const Layout& L = c->L;
     const OrbDims& d = L.orb;
-    const size_t fs = (size_t)L.cw * L.ch;
-    if (orb_phase1_launch(d, &c->orb0, L.frame_bytes, c->tab_dev, L.tab_off, nb, img, L.cw, fs, mask, L.cw, fs, st)) return 1;
     for (int f = 0; f < nb; f++)
         OVO_CUDA(cudaMemcpyAsync(c->h_lvl + 32 * f, (uint8_t*)c->orb0.lvl_count + L.frame_bytes * f, 17 * 4, cudaMemcpyDeviceToHost, st));
     OVO_CUDA(cudaStreamSynchronize(st));

@@ -467,8 +467,8 @@ __device__ __forceinline__ void wta_batch(const uint32_t* svec, int lane, const 
     for (int o = 1; o < 8; o <<= 1) kbest = min(kbest, __shfl_xor_sync(0xffffffffu, kbest, o));
     const int minS = (int)(kbest >> 9), best = (int)(kbest & 511u);
     // runner-up over |d - best| > 1: bit c of `near` marks this lane's c-th disparity as one of best-1, best, best+1
-    const uint32_t sh = (uint32_t)(best - q * 2 * NW + 1);  // position of best+1's successor bit; huge when out of range
-    const uint32_t near = sh < 32u ? ((7u << sh) >> 2) : 0u;
+    const uint32_t sh = (uint32_t)(best - q * 2 * NW + 1);  // bit of best+1, plus 2; huge (wrapped) when best lies far below
+    const uint32_t near = sh < 34u ? (uint32_t)((7ull << sh) >> 2) : 0u;  // 64-bit: a lane covers up to 32 disparities
     uint32_t m2 = 0xFFFFu;
 #pragma unroll
     for (int i = 0; i < NW; i++) {

@@ -167,6 +167,19 @@ class Engine:
                                                           kp.data_ptr(), desc.data_ptr(), n, self._stream()))
         return kp, desc, list(n)
 
+    def orb_begin(self, img, mask):
+        """First half of orb(): queue the detection phase (asynchronous).  Keep img / mask alive until orb_finish."""
+        N.check(self.lib, self.lib.ovo_orb_detect_begin(self.ctx, img.data_ptr(), None if mask is None else mask.data_ptr(),
+                                                        img.shape[0], self._stream()))
+
+    def orb_finish(self, nb):
+        """Second half of orb(): wait for the detection phase, select on the host, queue the descriptor phase."""
+        kp = torch.empty((nb, self.kp_cap, N.KP_FIELDS), dtype=torch.float32, device=self.device)
+        desc = torch.empty((nb, self.kp_cap, 32), dtype=torch.uint8, device=self.device)
+        n = (ctypes.c_int * nb)()
+        N.check(self.lib, self.lib.ovo_orb_detect_finish(self.ctx, nb, kp.data_ptr(), desc.data_ptr(), n, self._stream()))
+        return kp, desc, list(n)
+
     def knn2(self, desc_q, nq, desc_t, nt, out=None):
         nn = self.nn[0] if out is None else out
         N.check(self.lib, self.lib.ovo_knn2_hamming(self.ctx, desc_q.data_ptr(), nq, desc_t.data_ptr(), nt, nn.data_ptr(), self._stream()))
@@ -272,8 +285,17 @@ class Engine:
     # ---- whole-frame feature extraction ---------------------------------------------------------------------------------
     def frames(self, left, right):
         """left/right: device u8 [nb,H,W] (rectified, gray) -> list of Frame."""
+        return self.frames_finish(self.frames_begin(left, right))
+
+    def frames_begin(self, left, right):
+        """Queue disparity + detection for a batch without waiting (one batch in flight per engine) -> token for frames_finish."""
         disp16 = self.sgbm(left, right)
         disp, mask = self.disparity_post(disp16)
         img = self.crop(left)
-        kp, desc, n = self.orb(img, mask)
-        return [Frame(img[i], disp[i], kp[i], desc[i], n[i]) for i in range(left.shape[0])]
+        self.orb_begin(img, mask)
+        return (left, right, disp16, disp, mask, img)  # inputs and intermediates stay referenced while the device uses them
+
+    def frames_finish(self, token):
+        _, _, _, disp, _, img = token
+        kp, desc, n = self.orb_finish(img.shape[0])
+        return [Frame(img[i], disp[i], kp[i], desc[i], n[i]) for i in range(img.shape[0])]

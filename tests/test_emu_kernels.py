@@ -49,10 +49,16 @@ class Ctx:
     (190, 21, 128, 1, dict(uniquenessRatio=0)),                                  # odd height: the two-rows-per-warp kernel's tail
     (170, 19, 96, 1, dict(blockSize=3, P1=72, P2=288, disp12MaxDiff=2)),        # padded 96 -> 128
     (180, 18, 112, 1, dict(mode=1)),                                            # opt-in MODE_HH through the same kernel
+    (300, 17, 256, 1, dict(uniquenessRatio=5, _d=31)),                          # 256 disparities; true disparity at a selection-lane edge
+    (330, 16, 256, 1, dict(_d=62)),
+    (282, 16, 208, 1, dict(blockSize=3, P1=72, P2=288)),                        # padded 208 -> 256
+    (160, 20, 64, 1, dict(uniquenessRatio=100)),                                # uniquenessRatio >= 100: cell-by-cell selection
 ])
 def test_sgbm_kernels(emu, W, H, D, nb, kw):
+    kw = dict(kw)
+    shift = kw.pop("_d", 7)
     p = sgbm_params(D, **kw)
-    L, R = occluded_pair(W, H)
+    L, R = occluded_pair(W, H, d=shift)
     Ls = np.stack([np.roll(L, 3 * i, 1) for i in range(nb)])
     Rs = np.stack([np.roll(R, 3 * i, 1) for i in range(nb)])
     c = Ctx(emu, W, H, p, (0, 0, W, H), np.eye(4), 100, nb)

@@ -203,6 +203,42 @@ def test_batch_odometer_equals_single_stream(golden):
         assert bo.odometers[s].skipped_frames == singles[s].skipped_frames
 
 
+def test_batches_in_flight_round_robin_equals_update(golden):
+    """begin()/finish() with two batches in flight on two streams (the bench driver) == update() called step by step."""
+    import torch
+    from openvo_b200.batch import BatchOdometer
+    g = golden("seq_skip")
+    W, H, D, n = int(g["W"]), int(g["H"]), int(g["D"]), int(g["nfeatures"])
+    cam, _ = _cam(W, H, D)
+    S, G = 2, 2
+    nfr = len(g["left"])
+    steps = nfr + S * G - 1
+
+    def frames_of(step, grp):
+        idx = [min(max(step - (grp * S + s), 0), nfr - 1) for s in range(S)]
+        return g["left"][idx], g["right"][idx]
+    bos = [BatchOdometer(cam, S, nfeatures=n, engine_tag=10 + grp, preprocessed_frames=True) for grp in range(G)]
+    streams = [torch.cuda.Stream() for _ in range(G)]
+    got = [[] for _ in range(G)]
+    for grp in range(G):
+        with torch.cuda.stream(streams[grp]):
+            bos[grp].begin(*frames_of(0, grp))
+    for step in range(steps):
+        for grp in range(G):
+            with torch.cuda.stream(streams[grp]):
+                got[grp].append(bos[grp].finish())
+                if step + 1 < steps:
+                    bos[grp].begin(*frames_of(step + 1, grp))
+    torch.cuda.synchronize()
+    for grp in range(G):
+        ref = BatchOdometer(cam, S, nfeatures=n, engine_tag=20 + grp, preprocessed_frames=True)
+        want = [ref.update(*frames_of(step, grp)) for step in range(steps)]
+        assert got[grp] == want
+        for s in range(S):
+            assert np.array_equal(bos[grp].odometers[s].c_T_w, ref.odometers[s].c_T_w)
+            assert bos[grp].odometers[s].skip_cause == ref.odometers[s].skip_cause
+
+
 def test_rectify_and_gray_bit_exact():
     import cv2
     W, H = 480, 160
