@@ -74,29 +74,35 @@ __global__ void __launch_bounds__(256) k_orb_copy_level0(OrbDims d, OrbWorkspace
 }
 
 // ---- FAST-9/16 score ----------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int arc9_max_of_min(const int (&v)[16]) {
-    // max over the 16 arcs of (min over 9 consecutive ring values)
-    int m2[16], m4[16], m8[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) m2[k] = min(v[k], v[(k + 1) & 15]);
-#pragma unroll
-    for (int k = 0; k < 16; k++) m4[k] = min(m2[k], m2[(k + 2) & 15]);
-#pragma unroll
-    for (int k = 0; k < 16; k++) m8[k] = min(m4[k], m4[(k + 4) & 15]);
-    int best = -1000;
-#pragma unroll
-    for (int k = 0; k < 16; k++) best = max(best, min(m8[k], v[(k + 8) & 15]));
-    return best;
-}
-
 constexpr int kFastTX = 32, kFastTY = 16;  // tile of the fused FAST + NMS kernel (one 32-bit candidate word per tile row)
 
-__device__ __forceinline__ void fast_ring(const uint8_t (*tile)[kFastTX + 8], int cx, int cy, int (&v)[16]) {
-    const int c = tile[cy][cx];
-    v[0] = c - tile[cy + 3][cx];      v[1] = c - tile[cy + 3][cx + 1];  v[2] = c - tile[cy + 2][cx + 2];  v[3] = c - tile[cy + 1][cx + 3];
-    v[4] = c - tile[cy][cx + 3];      v[5] = c - tile[cy - 1][cx + 3];  v[6] = c - tile[cy - 2][cx + 2];  v[7] = c - tile[cy - 3][cx + 1];
-    v[8] = c - tile[cy - 3][cx];      v[9] = c - tile[cy - 3][cx - 1];  v[10] = c - tile[cy - 2][cx - 2]; v[11] = c - tile[cy - 1][cx - 3];
-    v[12] = c - tile[cy][cx - 3];     v[13] = c - tile[cy + 1][cx - 3]; v[14] = c - tile[cy + 2][cx - 2]; v[15] = c - tile[cy + 3][cx - 1];
+// FAST-9/16 score of the pixel at (cx, cy) of a shared-memory tile: the largest threshold for which it is still a corner
+// = max over the 16 arcs of (min over 9 consecutive ring differences), for the brighter and the darker polarity, minus 1;
+// 0 when that is below the detection threshold.  Both polarities ride in one register: with u = centre - ring + 256 (> 0)
+// the word u * (1 - 2^16) + (512 << 16) holds (centre - ring) + 256 in its low half and (ring - centre) + 256 in its high
+// half, so one multiply-add per ring pixel packs them and the arc minima / maxima are packed unsigned 16-bit operations.
+__device__ __forceinline__ int fast_score(const uint8_t (*tile)[kFastTX + 8], int cx, int cy) {
+    const uint32_t ck = (uint32_t)(tile[cy][cx] + 256) * 0xFFFF0001u + (512u << 16);
+    auto pk = [&](int dy, int dx) -> uint32_t { return (uint32_t)tile[cy + dy][cx + dx] * 0x0000FFFFu + ck; };
+    uint32_t w[16];
+    w[0] = pk(3, 0);   w[1] = pk(3, 1);   w[2] = pk(2, 2);    w[3] = pk(1, 3);
+    w[4] = pk(0, 3);   w[5] = pk(-1, 3);  w[6] = pk(-2, 2);   w[7] = pk(-3, 1);
+    w[8] = pk(-3, 0);  w[9] = pk(-3, -1); w[10] = pk(-2, -2); w[11] = pk(-1, -3);
+    w[12] = pk(0, -3); w[13] = pk(1, -3); w[14] = pk(2, -2);  w[15] = pk(3, -1);
+    uint32_t m2[16], m4[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) m2[k] = __vminu2(w[k], w[(k + 1) & 15]);
+#pragma unroll
+    for (int k = 0; k < 16; k++) m4[k] = __vminu2(m2[k], m2[(k + 2) & 15]);
+    uint32_t best = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k += 2) {  // min over ring[k .. k+8] = min(m4[k], m4[k+4], ring[k+8])
+        const uint32_t a = __vimin3_u16x2(m4[k], m4[(k + 4) & 15], w[(k + 8) & 15]);
+        const uint32_t b = __vimin3_u16x2(m4[k + 1], m4[(k + 5) & 15], w[(k + 9) & 15]);
+        best = __vimax3_u16x2(best, a, b);
+    }
+    const int m = (int)max(best & 0xFFFFu, best >> 16) - 256;
+    return m > kFastT ? m - 1 : 0;
 }
 
 // Tiles of every level are numbered consecutively (level-major, then row-major), so one grid covers the whole pyramid
@@ -112,17 +118,14 @@ __device__ __forceinline__ void orb_flat_tile(const int (&off)[ORB_NLEVELS + 1],
     tx = t - ty * nx;
 }
 
-// FAST score + 3x3 NMS + border + mask, fused per 32x16 tile.  Pass A: the 9-contiguous test on brighter / darker bit
-// masks for every pixel of the tile plus a one-pixel apron (non-corners score 0), corners are queued in shared memory;
-// pass B scores the queue (max over arcs of min over 9, the expensive part, runs densely on corners only); pass C: a pixel
-// is a candidate when its score strictly beats its 8 neighbours, it lies inside the 31-pixel border and the mask is set.
+// FAST score + 3x3 NMS + border + mask, fused per 32x16 tile.  Every pixel of the tile plus a one-pixel apron is scored
+// (dense, no corner queue: with packed arithmetic the score costs less than a separate corner test); then a pixel is a
+// candidate when its score strictly beats its 8 neighbours, it lies inside the 31-pixel border and the mask is set.
 // Output: one bit per pixel (a 32-bit word per tile row, bit i = column x0 + i) and the score byte of each candidate.
 __global__ void __launch_bounds__(256) k_orb_fast_nms(OrbDims d, OrbWorkspace ws, size_t ws_stride, int has_mask) {
     constexpr int TX = kFastTX, TY = kFastTY, SW = TX + 2, SH = TY + 2;
     __shared__ uint8_t tile[TY + 8][kFastTX + 8];
     __shared__ uint8_t sc[SH][SW + 2];
-    __shared__ uint16_t queue[SW * SH];
-    __shared__ int nq;
     int level, bx, by;
     orb_flat_tile(d.fast_tiles, d, TX, blockIdx.x, level, bx, by);
     const int f = blockIdx.y;
@@ -137,61 +140,19 @@ __global__ void __launch_bounds__(256) k_orb_fast_nms(OrbDims d, OrbWorkspace ws
         return;
     }
     const uint8_t* img = fptr(ws.pyr, ws_stride, f) + L.off;
-    if (tid == 0) nq = 0;
     for (int i = tid; i < (TY + 8) * (TX + 8); i += 256) {
         const int ty = i / (TX + 8), tx = i - ty * (TX + 8);
         const int gx = min(max(x0 + tx - 4, 0), L.w - 1), gy = min(max(y0 + ty - 4, 0), L.h - 1);
         tile[ty][tx] = img[(size_t)gy * L.w + gx];
     }
     __syncthreads();
-    // pass A over the tile + apron; scores outside [kEdge-1, w-kEdge] are never read by a candidate, so they are skipped
-    for (int i0 = 0; i0 < SW * SH; i0 += 256) {
-        const int i = i0 + tid;
-        bool corner = false;
-        int sx = 0, sy = 0;
-        if (i < SW * SH) {
-            sy = i / SW;
-            sx = i - sy * SW;
-            const int x = x0 - 1 + sx, y = y0 - 1 + sy;
-            if (x >= kEdge - 1 && x <= L.w - kEdge && y >= kEdge - 1 && y <= L.h - kEdge) {
-                int v[16];
-                fast_ring(tile, sx + 3, sy + 3, v);  // v[k] = centre - ring[k]
-                uint32_t mb = 0, md = 0;
-#pragma unroll
-                for (int k = 0; k < 16; k++) {
-                    if (v[k] > kFastT) mb |= 1u << k;
-                    if (v[k] < -kFastT) md |= 1u << k;
-                }
-                auto has9 = [](uint32_t m) {
-                    m |= m << 16;
-                    uint32_t t = m & (m >> 1);
-                    t &= t >> 2;
-                    t &= t >> 4;
-                    t &= m >> 8;
-                    return (t & 0xFFFFu) != 0;
-                };
-                corner = has9(mb) || has9(md);
-            }
-            if (!corner) sc[sy][sx] = 0;
-        }
-        const uint32_t bal = __ballot_sync(0xffffffffu, corner);
-        if (bal) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&nq, __popc(bal));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (corner) queue[base + __popc(bal & ((1u << lane) - 1))] = (uint16_t)i;
-        }
-    }
-    __syncthreads();
-    const int n = nq;
-    for (int i = tid; i < n; i += 256) {
-        const int t = queue[i], sy = t / SW, sx = t - sy * SW;
-        int v[16], nv[16];
-        fast_ring(tile, sx + 3, sy + 3, v);
-#pragma unroll
-        for (int k = 0; k < 16; k++) nv[k] = -v[k];
-        const int m = max(arc9_max_of_min(v), arc9_max_of_min(nv));
-        sc[sy][sx] = (uint8_t)(m - 1);  // largest threshold for which the pixel is still a corner
+    // scores outside [kEdge-1, w-kEdge] x [kEdge-1, h-kEdge] are never read by a candidate: left at 0
+    for (int i = tid; i < SW * SH; i += 256) {
+        const int sy = i / SW, sx = i - sy * SW;
+        const int x = x0 - 1 + sx, y = y0 - 1 + sy;
+        int v = 0;
+        if (x >= kEdge - 1 && x <= L.w - kEdge && y >= kEdge - 1 && y <= L.h - kEdge) v = fast_score(tile, sx + 3, sy + 3);
+        sc[sy][sx] = (uint8_t)v;
     }
     __syncthreads();
     const uint8_t* mk = has_mask ? fptr(ws.maskpyr, ws_stride, f) + L.off : nullptr;

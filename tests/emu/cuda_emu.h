@@ -260,6 +260,8 @@ static inline unsigned emu_h2(unsigned a, unsigned b, unsigned (*op)(unsigned, u
 }
 static inline unsigned __vminu2(unsigned a, unsigned b) { return emu_h2(a, b, [](unsigned x, unsigned y) { return std::min(x, y); }); }
 static inline unsigned __vmaxu2(unsigned a, unsigned b) { return emu_h2(a, b, [](unsigned x, unsigned y) { return std::max(x, y); }); }
+static inline unsigned __vimin3_u16x2(unsigned a, unsigned b, unsigned c) { return __vminu2(__vminu2(a, b), c); }
+static inline unsigned __vimax3_u16x2(unsigned a, unsigned b, unsigned c) { return __vmaxu2(__vmaxu2(a, b), c); }
 static inline unsigned __viaddmin_u16x2(unsigned a, unsigned b, unsigned c) {
     const unsigned lo = std::min(((a & 0xFFFF) + (b & 0xFFFF)) & 0xFFFF, c & 0xFFFF);
     const unsigned hi = std::min(((a >> 16) + (b >> 16)) & 0xFFFF, c >> 16);
