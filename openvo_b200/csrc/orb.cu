@@ -140,10 +140,18 @@ __global__ void __launch_bounds__(256) k_orb_fast_nms(OrbDims d, OrbWorkspace ws
         return;
     }
     const uint8_t* img = fptr(ws.pyr, ws_stride, f) + L.off;
-    for (int i = tid; i < (TY + 8) * (TX + 8); i += 256) {
-        const int ty = i / (TX + 8), tx = i - ty * (TX + 8);
-        const int gx = min(max(x0 + tx - 4, 0), L.w - 1), gy = min(max(y0 + ty - 4, 0), L.h - 1);
-        tile[ty][tx] = img[(size_t)gy * L.w + gx];
+    if (x0 >= 4 && x0 + TX + 4 <= L.w && y0 >= 4 && y0 + TY + 4 <= L.h) {  // interior tile: no clamping
+        const uint8_t* base = img + (size_t)(y0 - 4) * L.w + (x0 - 4);
+        for (int i = tid; i < (TY + 8) * (TX + 8); i += 256) {
+            const int ty = i / (TX + 8), tx = i - ty * (TX + 8);
+            tile[ty][tx] = base[ty * L.w + tx];
+        }
+    } else {
+        for (int i = tid; i < (TY + 8) * (TX + 8); i += 256) {
+            const int ty = i / (TX + 8), tx = i - ty * (TX + 8);
+            const int gx = min(max(x0 + tx - 4, 0), L.w - 1), gy = min(max(y0 + ty - 4, 0), L.h - 1);
+            tile[ty][tx] = img[(size_t)gy * L.w + gx];
+        }
     }
     __syncthreads();
     // scores outside [kEdge-1, w-kEdge] x [kEdge-1, h-kEdge] are never read by a candidate: left at 0
@@ -324,7 +332,7 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 }
 
 __global__ void __launch_bounds__(256) k_orb_blur(OrbDims d, OrbWorkspace ws, size_t ws_stride) {
-    __shared__ uint8_t src[kBlurTY + 6][kBlurTX + 8];
+    __shared__ __align__(4) uint8_t src[kBlurTY + 6][kBlurTX + 8];
     __shared__ float rows[kBlurTY + 6][kBlurTX];
     int level, bx, by;
     orb_flat_tile(d.blur_tiles, d, kBlurTX, blockIdx.x, level, bx, by);
@@ -332,46 +340,75 @@ __global__ void __launch_bounds__(256) k_orb_blur(OrbDims d, OrbWorkspace ws, si
     const OrbLevel L = d.lv[level];
     const int x0 = bx * kBlurTX, y0 = by * kBlurTY;
     const uint8_t* img = fptr(ws.pyr, ws_stride, f) + L.off;
-    for (int i = threadIdx.x; i < (kBlurTY + 6) * (kBlurTX + 6); i += 256) {
-        const int ty = i / (kBlurTX + 6), tx = i % (kBlurTX + 6);
-        src[ty][tx] = img[(size_t)reflect101(y0 + ty - 3, L.h) * L.w + reflect101(x0 + tx - 3, L.w)];
+    if (x0 >= 3 && x0 + kBlurTX + 3 <= L.w && y0 >= 3 && y0 + kBlurTY + 3 <= L.h) {  // interior tile: no border reflection
+        const uint8_t* base = img + (size_t)(y0 - 3) * L.w + (x0 - 3);
+        for (int i = threadIdx.x; i < (kBlurTY + 6) * (kBlurTX + 6); i += 256) {
+            const int ty = i / (kBlurTX + 6), tx = i - ty * (kBlurTX + 6);
+            src[ty][tx] = base[ty * L.w + tx];
+        }
+    } else {
+        for (int i = threadIdx.x; i < (kBlurTY + 6) * (kBlurTX + 6); i += 256) {
+            const int ty = i / (kBlurTX + 6), tx = i - ty * (kBlurTX + 6);
+            src[ty][tx] = img[(size_t)reflect101(y0 + ty - 3, L.h) * L.w + reflect101(x0 + tx - 3, L.w)];
+        }
     }
     __syncthreads();
     const float k0 = c_gk[0], k1 = c_gk[1], k2 = c_gk[2], k3 = c_gk[3];
     const int wbody = (L.w / 32) * 32, wcol = (L.w / 4) * 4;
-    for (int i = threadIdx.x; i < (kBlurTY + 6) * kBlurTX; i += 256) {
-        const int ty = i / kBlurTX, tx = i % kBlurTX;
-        const float p0 = src[ty][tx], p1 = src[ty][tx + 1], p2 = src[ty][tx + 2], p3 = src[ty][tx + 3], p4 = src[ty][tx + 4],
-                    p5 = src[ty][tx + 5], p6 = src[ty][tx + 6];
-        float acc;
-        if (x0 + tx < wbody) {
-            acc = __fmaf_rn(k0, p0, 0.f);
-            acc = __fmaf_rn(k1, p1, acc); acc = __fmaf_rn(k2, p2, acc); acc = __fmaf_rn(k3, p3, acc);
-            acc = __fmaf_rn(k2, p4, acc); acc = __fmaf_rn(k1, p5, acc); acc = __fmaf_rn(k0, p6, acc);
-        } else {
-            acc = __fmul_rn(k0, p0);
-            acc = __fadd_rn(acc, __fmul_rn(k1, p1)); acc = __fadd_rn(acc, __fmul_rn(k2, p2)); acc = __fadd_rn(acc, __fmul_rn(k3, p3));
-            acc = __fadd_rn(acc, __fmul_rn(k2, p4)); acc = __fadd_rn(acc, __fmul_rn(k1, p5)); acc = __fadd_rn(acc, __fmul_rn(k0, p6));
+    // row pass: a thread produces 4 adjacent outputs of a row from 10 source bytes (three aligned words)
+    for (int i = threadIdx.x; i < (kBlurTY + 6) * (kBlurTX / 4); i += 256) {
+        const int ty = i / (kBlurTX / 4), tx = (i - ty * (kBlurTX / 4)) * 4;
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(&src[ty][tx]);
+        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+        float p[10];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            p[j] = (float)((w0 >> (8 * j)) & 0xFFu);
+            p[4 + j] = (float)((w1 >> (8 * j)) & 0xFFu);
         }
-        rows[ty][tx] = acc;
+        p[8] = (float)(w2 & 0xFFu);
+        p[9] = (float)((w2 >> 8) & 0xFFu);
+#pragma unroll
+        for (int o = 0; o < 4; o++) {
+            float acc;
+            if (x0 + tx + o < wbody) {
+                acc = __fmaf_rn(k0, p[o], 0.f);
+                acc = __fmaf_rn(k1, p[o + 1], acc); acc = __fmaf_rn(k2, p[o + 2], acc); acc = __fmaf_rn(k3, p[o + 3], acc);
+                acc = __fmaf_rn(k2, p[o + 4], acc); acc = __fmaf_rn(k1, p[o + 5], acc); acc = __fmaf_rn(k0, p[o + 6], acc);
+            } else {
+                acc = __fmul_rn(k0, p[o]);
+                acc = __fadd_rn(acc, __fmul_rn(k1, p[o + 1])); acc = __fadd_rn(acc, __fmul_rn(k2, p[o + 2]));
+                acc = __fadd_rn(acc, __fmul_rn(k3, p[o + 3])); acc = __fadd_rn(acc, __fmul_rn(k2, p[o + 4]));
+                acc = __fadd_rn(acc, __fmul_rn(k1, p[o + 5])); acc = __fadd_rn(acc, __fmul_rn(k0, p[o + 6]));
+            }
+            rows[ty][tx + o] = acc;
+        }
     }
     __syncthreads();
+    // column pass: a thread produces 4 consecutive outputs of a column from 10 row sums
     uint8_t* out = fptr(ws.blur, ws_stride, f) + L.off;
-    for (int i = threadIdx.x; i < kBlurTY * kBlurTX; i += 256) {
-        const int ty = i / kBlurTX, tx = i % kBlurTX;
-        const int x = x0 + tx, y = y0 + ty;
-        if (x >= L.w || y >= L.h) continue;
-        float c = __fmul_rn(k3, rows[ty + 3][tx]);
-        const float s1 = __fadd_rn(rows[ty + 4][tx], rows[ty + 2][tx]);
-        const float s2 = __fadd_rn(rows[ty + 5][tx], rows[ty + 1][tx]);
-        const float s3 = __fadd_rn(rows[ty + 6][tx], rows[ty][tx]);
-        if (x < wcol) {
-            c = __fmaf_rn(k2, s1, c); c = __fmaf_rn(k1, s2, c); c = __fmaf_rn(k0, s3, c);
-        } else {
-            c = __fadd_rn(c, __fmul_rn(k2, s1)); c = __fadd_rn(c, __fmul_rn(k1, s2)); c = __fadd_rn(c, __fmul_rn(k0, s3));
+    {
+        const int tx = threadIdx.x % kBlurTX, tyb = (threadIdx.x / kBlurTX) * 4;
+        const int x = x0 + tx;
+        float r[10];
+#pragma unroll
+        for (int j = 0; j < 10; j++) r[j] = rows[tyb + j][tx];
+#pragma unroll
+        for (int o = 0; o < 4; o++) {
+            const int y = y0 + tyb + o;
+            if (x >= L.w || y >= L.h) continue;
+            float c = __fmul_rn(k3, r[o + 3]);
+            const float s1 = __fadd_rn(r[o + 4], r[o + 2]);
+            const float s2 = __fadd_rn(r[o + 5], r[o + 1]);
+            const float s3 = __fadd_rn(r[o + 6], r[o]);
+            if (x < wcol) {
+                c = __fmaf_rn(k2, s1, c); c = __fmaf_rn(k1, s2, c); c = __fmaf_rn(k0, s3, c);
+            } else {
+                c = __fadd_rn(c, __fmul_rn(k2, s1)); c = __fadd_rn(c, __fmul_rn(k1, s2)); c = __fadd_rn(c, __fmul_rn(k0, s3));
+            }
+            const int v = __float2int_rn(c);
+            out[(size_t)y * L.w + x] = (uint8_t)min(max(v, 0), 255);
         }
-        const int v = __float2int_rn(c);
-        out[(size_t)y * L.w + x] = (uint8_t)min(max(v, 0), 255);
     }
 }
 

@@ -37,34 +37,44 @@ constexpr int kEPT = 4;  // pixels per thread of the small per-pixel kernels (CT
 
 __global__ void __launch_bounds__(256) k_sgbm_prep(const uint8_t* __restrict__ left, const uint8_t* __restrict__ right, int pitch,
                                                    size_t frame_stride, SgbmDims d, SgbmWorkspace ws, size_t ws_stride) {
+    // one thread = 4 adjacent pixels of a row: 3 rows x 8 bytes are loaded once and shared by the 6 gradients they need
     const int f = blockIdx.y >> 1, im = blockIdx.y & 1;
-    const int W = d.W, H = d.H, ftzero = d.ftzero, n = W * H;
+    const int W = d.W, H = d.H, ftzero = d.ftzero;
+    const int QW = (W + 3) >> 2;
+    const int q = blockIdx.x * 256 + threadIdx.x;
+    if (q >= QW * H) return;
+    const int y = q / QW, x0 = (q - y * QW) * 4;
     const uint8_t* I = (im ? right : left) + frame_stride * (size_t)f;
-    uint2* out = reinterpret_cast<uint2*>(frame_ptr(ws.prep, ws_stride, f)) + (size_t)im * n;
+    const uint8_t* rows[3] = {I + (size_t)y * pitch, I + (size_t)max(y - 1, 0) * pitch, I + (size_t)min(y + 1, H - 1) * pitch};
+    int a[3][8];
 #pragma unroll
-    for (int e = 0; e < kEPT; e++) {
-        const int i = (blockIdx.x * kEPT + e) * 256 + threadIdx.x;
-        if (i >= n) break;
-        const int y = i / W, x = i - y * W;
-        const uint8_t* r = I + (size_t)y * pitch;
-        const uint8_t* rn = I + (size_t)max(y - 1, 0) * pitch;
-        const uint8_t* rs = I + (size_t)min(y + 1, H - 1) * pitch;
-        auto G = [&](int xx) -> int {
-            if (xx <= 0 || xx >= W - 1) return ftzero;
-            int v = 2 * ((int)r[xx + 1] - (int)r[xx - 1]) + ((int)rn[xx + 1] - (int)rn[xx - 1]) + ((int)rs[xx + 1] - (int)rs[xx - 1]);
-            return min(max(v, -ftzero), ftzero) + ftzero;
-        };
-        auto R = [&](int xx) -> int { return (xx <= 0 || xx >= W - 1) ? ftzero : (int)r[xx]; };
+    for (int k = 0; k < 3; k++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) a[k][j] = rows[k][min(max(x0 - 2 + j, 0), W - 1)];
+    int G[6], R[6];  // clipped Sobel-x + ftzero, and the raw value, at x0-1 .. x0+4 (ftzero on the border columns)
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        const int xx = x0 - 1 + j;
+        const bool border = xx <= 0 || xx >= W - 1;
+        const int v = 2 * (a[0][j + 2] - a[0][j]) + (a[1][j + 2] - a[1][j]) + (a[2][j + 2] - a[2][j]);
+        G[j] = border ? ftzero : min(max(v, -ftzero), ftzero) + ftzero;
+        R[j] = border ? ftzero : a[0][j + 1];
+    }
+    uint2* out = reinterpret_cast<uint2*>(frame_ptr(ws.prep, ws_stride, f)) + (size_t)im * H * W + (size_t)y * W;
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+        const int x = x0 + p;
+        if (x >= W) break;
         uint2 o;
         {
-            int c = G(x), vl = x > 0 ? (c + G(x - 1)) >> 1 : c, vr = x < W - 1 ? (c + G(x + 1)) >> 1 : c;
+            const int c = G[p + 1], vl = x > 0 ? (c + G[p]) >> 1 : c, vr = x < W - 1 ? (c + G[p + 2]) >> 1 : c;
             o.x = (uint32_t)c | ((uint32_t)min(min(vl, vr), c) << 8) | ((uint32_t)max(max(vl, vr), c) << 16);
         }
         {
-            int c = R(x), vl = x > 0 ? (c + R(x - 1)) >> 1 : c, vr = x < W - 1 ? (c + R(x + 1)) >> 1 : c;
+            const int c = R[p + 1], vl = x > 0 ? (c + R[p]) >> 1 : c, vr = x < W - 1 ? (c + R[p + 2]) >> 1 : c;
             o.y = (uint32_t)c | ((uint32_t)min(min(vl, vr), c) << 8) | ((uint32_t)max(max(vl, vr), c) << 16);
         }
-        out[i] = o;
+        out[x] = o;
     }
 }
 
@@ -967,7 +977,7 @@ int sgbm_launch(const SgbmDims& d, const SgbmWorkspace* ws0, size_t ws_stride, i
                 int pitch, size_t frame_stride, int16_t* disp_out, cudaStream_t st) {
     const SgbmWorkspace& ws = *ws0;
     {
-        dim3 grid(cdiv(d.W * d.H, 256 * kEPT), nb * 2);
+        dim3 grid(cdiv(((d.W + 3) / 4) * d.H, 256), nb * 2);
         OVO_LAUNCH(k_sgbm_prep, grid, dim3(256), 0, st, left, right, pitch, frame_stride, d, ws, ws_stride);
         OVO_LAUNCH_CHECK();
     }

@@ -1,4 +1,4 @@
-timeout 1200 python -m pytest tests -q -m gpu -k "orb or update or batch or smoke" 2>&1 | tail -2
+timeout 1200 python -m pytest tests -q -m gpu -k "orb or update" 2>&1 | tail -2
 for i in 1 2; do
 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/sw.json 2> gpurun_out/sw.err
 python - <<P
