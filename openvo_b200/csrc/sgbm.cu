@@ -8,8 +8,9 @@
 //   k_sgbm_cost   prep   -> C[y][x1][d] int16 : Birchfield-Tomasi cost summed over the blockSize^2 window (A.4.2)
 //   k_sgbm_vert   C      -> Lv[3][y][x1][d]   : paths from (x-1,y-1), (x,y-1), (x+1,y-1); one warp per scan line
 //   k_sgbm_horiz  C, Lv  -> raw disparity     : paths from (x-1,y) and (x+1,y) run towards each other by two warps
-//                                               per row; whoever reaches a cell second owns the complete 5-path sum
-//                                               and does WTA / uniqueness / sub-pixel / disp2; then the LR check
+//                                               per row, parking their state every 4 cells; whoever reaches a cell
+//                                               second replays the other's path from the checkpoint, owns the complete
+//                                               5-path sum and does WTA / uniqueness / sub-pixel / disp2; then the LR check
 //   k_median3, k_ccl_*   -> 3x3 median and speckle filter (connected components, union-find)
 // All cost arithmetic is packed 2 x u16 per register on the DPX pipe (VIADDMNMX.U16x2 / VIMNMX.U16x2); the per-cell
 // minimum is one CREDUX.MIN.  No tensor cores: nothing here is a contraction.
