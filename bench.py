@@ -406,7 +406,7 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": workload, "frames_per_step": S * world, "sequences_per_gpu": S, "host_threads": NT, "batches_in_flight_per_thread": NG,
                            "sequences_per_batch": SP, "distinct_frames": N_DISTINCT,
-                           "l2_policy": "inputs+working set larger than L2: %d frames x ~0.55 GB SGBM volumes per step" % S,
+                           "l2_policy": "inputs+working set larger than L2: %d frames x ~0.47 GB SGBM volumes per step" % S,
                            "frames_committed": dev["ok"]},
                 "clocks": dev["clocks"], "gpu_launches": dev["launches"],
                 "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],

@@ -188,20 +188,6 @@ class Engine:
     def pair_async(self, a, b, match_threshold, slot=0, cross_check=False):
         return self.pair_batch_async([(a, b, slot)], match_threshold, cross_check)
 
-    def _pair_async_seams(self, a, b, match_threshold, slot=0):
-        """Frames a (query) and b (train): 2-NN + ratio + fused 3-D lookup + rigid alignment, all on the device; results
-        land in pair_out[slot].  Nothing is read back until pair_collect()."""
-        st = self._stream()
-        nn, out = self.nn[slot], self.pair_out[slot]
-        N.check(self.lib, self.lib.ovo_knn2_hamming(self.ctx, a.desc.data_ptr(), a.n_kp, b.desc.data_ptr(), b.n_kp, nn.data_ptr(), st))
-        counts_ptr = out.data_ptr() + 16 * 8
-        N.check(self.lib, self.lib.ovo_match_points(self.ctx, nn.data_ptr(), a.n_kp, float(match_threshold), a.kp.data_ptr(),
-                                                    b.kp.data_ptr(), a.disp.data_ptr(), b.disp.data_ptr(),
-                                                    self.matches[slot].data_ptr(), self.pts1[slot].data_ptr(),
-                                                    self.pts2[slot].data_ptr(), counts_ptr, None, st))
-        N.check(self.lib, self.lib.ovo_rigid_transform(self.ctx, self.pts1[slot].data_ptr(), self.pts2[slot].data_ptr(), counts_ptr,
-                                                       self.kp_cap, out.data_ptr(), st))
-
     def pair_batch_async(self, jobs, match_threshold, cross_check=False):
         """jobs: list of (frame a, frame b, slot).  All pairs in four launches (ovo_pair_batch); results land in pair_out[slot]."""
         if not jobs:
