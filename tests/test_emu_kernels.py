@@ -285,6 +285,21 @@ def test_sgbm_kernels_random_small(emu):
         assert np.array_equal(out[0], O.sgbm_compute(L, R, p)), (trial, W, H, D, kw)
 
 
+def test_sgbm_kernels_tiny_widths(emu):
+    """W - D of 1..13 columns: empty phases, a lone partial segment, rendezvous at the row ends (both modes)."""
+    for D, w1s in ((16, (8, 9, 12, 13)), (64, (1, 2, 3, 4, 5, 7, 8, 9, 13))):
+        for w1 in w1s:
+            for mode in (0, 1):
+                W, H = D + w1, 17
+                p = sgbm_params(D, uniquenessRatio=5)
+                p["mode"] = mode
+                L, R = occluded_pair(W, H, d=3)
+                c = Ctx(emu, W, H, p, (0, 0, W, H), np.eye(4), 100)
+                out = np.zeros((1, H, W), np.int16)
+                N.check(emu, emu.ovo_sgbm_compute(c.ctx, N.ptr(L), N.ptr(R), W, W * H, 1, N.ptr(out), None))
+                assert np.array_equal(out[0], O.sgbm_compute_mode(L, R, p, mode)), (D, w1, mode)
+
+
 def _pnp_case(seed=0, m=500, n_out=120):
     from oracle import pnp_restate as P
     rng = np.random.default_rng(seed)
