@@ -68,7 +68,8 @@ def test_sgbm_kernels(emu, W, H, D, nb, kw):
         assert np.array_equal(out[f], O.sgbm_compute_mode(Ls[f], Rs[f], p, p.get("mode", 0)))
 
 
-@pytest.mark.parametrize("W,H,n,usemask,nb", [(320, 120, 300, False, 1), (300, 170, 300, True, 2)])
+@pytest.mark.parametrize("W,H,n,usemask,nb", [(320, 120, 300, False, 1), (300, 170, 300, True, 2), (161, 97, 150, True, 1),
+                                              (257, 66, 200, False, 1), (96, 230, 120, True, 1)])
 def test_orb_kernels(emu, W, H, n, usemask, nb):
     c = Ctx(emu, W, H, sgbm_params(16), (0, 0, W, H), np.eye(4), n, nb)
     L, R = synth.kat_pair(W, H)
