@@ -49,6 +49,7 @@ class Ctx:
     (190, 21, 128, 1, dict(uniquenessRatio=0)),                                  # odd height: the two-rows-per-warp kernel's tail
     (170, 19, 96, 1, dict(blockSize=3, P1=72, P2=288, disp12MaxDiff=2)),        # padded 96 -> 128
     (180, 18, 112, 1, dict(mode=1)),                                            # opt-in MODE_HH through the same kernel
+    (214, 70, 64, 1, dict(uniquenessRatio=5, _d=9)),                            # three 32-row bands x three 64-column blocks of the fused vertical kernel
     (300, 17, 256, 1, dict(uniquenessRatio=5, _d=31)),                          # 256 disparities; true disparity at a selection-lane edge
     (330, 16, 256, 1, dict(_d=62)),
     (282, 16, 208, 1, dict(blockSize=3, P1=72, P2=288)),                        # padded 208 -> 256
