@@ -299,19 +299,28 @@ __global__ void __launch_bounds__(128) k_orb_harris(OrbDims d, OrbWorkspace ws, 
     const uint8_t* img = fptr(ws.pyr, ws_stride, f) + L.off;
     const int xy = fptr(ws.cand_xy, ws_stride, f)[i];
     const int x0 = xy & 0xFFFF, y0 = xy >> 16;
+    // 7x7 window of 3x3 Sobel responses = a 9x9 patch: three rows of 9 pixels slide down in registers (81 loads, not 392)
     int a = 0, b = 0, c = 0;
-    for (int y = y0 - 3; y <= y0 + 3; y++) {
-        const uint8_t* rm = img + (size_t)(y - 1) * L.w + x0;
-        const uint8_t* r0 = rm + L.w;
-        const uint8_t* rp = r0 + L.w;
+    const uint8_t* p = img + (size_t)(y0 - 4) * L.w + (x0 - 4);
+    int rm[9], r0[9], rp[9];
 #pragma unroll
-        for (int dx = -3; dx <= 3; dx++) {
-            const int Ix = 2 * ((int)r0[dx + 1] - (int)r0[dx - 1]) + ((int)rm[dx + 1] - (int)rm[dx - 1]) + ((int)rp[dx + 1] - (int)rp[dx - 1]);
-            const int Iy = 2 * ((int)rp[dx] - (int)rm[dx]) + ((int)rp[dx - 1] - (int)rm[dx - 1]) + ((int)rp[dx + 1] - (int)rm[dx + 1]);
+    for (int k = 0; k < 9; k++) { rm[k] = p[k]; r0[k] = p[L.w + k]; }
+    p += 2 * L.w;
+#pragma unroll
+    for (int row = 0; row < 7; row++) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) rp[k] = p[k];
+        p += L.w;
+#pragma unroll
+        for (int k = 1; k <= 7; k++) {
+            const int Ix = 2 * (r0[k + 1] - r0[k - 1]) + (rm[k + 1] - rm[k - 1]) + (rp[k + 1] - rp[k - 1]);
+            const int Iy = 2 * (rp[k] - rm[k]) + (rp[k - 1] - rm[k - 1]) + (rp[k + 1] - rm[k + 1]);
             a += Ix * Ix;
             b += Iy * Iy;
             c += Ix * Iy;
         }
+#pragma unroll
+        for (int k = 0; k < 9; k++) { rm[k] = r0[k]; r0[k] = rp[k]; }
     }
     const float scale = __fdiv_rn(1.f, 4.f * 7.f * 255.f);
     const float s4 = __fmul_rn(__fmul_rn(__fmul_rn(scale, scale), scale), scale);
