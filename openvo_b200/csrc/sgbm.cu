@@ -785,30 +785,37 @@ __global__ void __launch_bounds__(64, NPR == 4 ? 6 : OVO_HOR_MINB) k_sgbm_horiz(
 // ------------------------------------------------------------------------------------------------------------
 // A.4.6 post filters
 // ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cswap(int& a, int& b) { const int t = min(a, b); b = max(a, b); a = t; }
+// packed compare-exchange: both 16-bit halves (two adjacent pixels) at once
+__device__ __forceinline__ void cswap2(uint32_t& a, uint32_t& b) { const uint32_t t = __vmins2(a, b); b = __vmaxs2(a, b); a = t; }
 
 __global__ void __launch_bounds__(256) k_median3(const int16_t* __restrict__ src, size_t src_stride, int16_t* __restrict__ dst,
                                                  size_t dst_stride, int W, int H) {
-    const int f = blockIdx.y, n = W * H;
-    const int16_t* s = frame_ptr(src, src_stride, f);
+    // a thread filters two horizontally adjacent pixels: low half = pixel x, high half = pixel x + 1
+    const int f = blockIdx.y, PW = (W + 1) >> 1, n = PW * H;
+    const uint16_t* s = reinterpret_cast<const uint16_t*>(frame_ptr(src, src_stride, f));
     int16_t* o = frame_ptr(dst, dst_stride, f);
 #pragma unroll
     for (int e = 0; e < kEPT; e++) {
         const int i = (blockIdx.x * kEPT + e) * 256 + threadIdx.x;
         if (i >= n) break;
-        const int y = i / W, x = i - y * W;
-        int v[9];
+        const int y = i / PW, x = (i - y * PW) * 2;
+        const int xm = max(x - 1, 0), x1 = min(x + 1, W - 1), x2 = min(x + 2, W - 1);
+        uint32_t v[9];
 #pragma unroll
-        for (int dy = -1; dy <= 1; dy++)
-#pragma unroll
-            for (int dx = -1; dx <= 1; dx++)
-                v[(dy + 1) * 3 + dx + 1] = s[(size_t)min(max(y + dy, 0), H - 1) * W + min(max(x + dx, 0), W - 1)];
+        for (int dy = -1; dy <= 1; dy++) {
+            const uint16_t* r = s + (size_t)min(max(y + dy, 0), H - 1) * W;
+            const uint32_t a = r[xm], b = r[x], c = r[x1], d = r[x2];
+            v[(dy + 1) * 3 + 0] = a | (b << 16);   // left neighbours of (x, x+1)
+            v[(dy + 1) * 3 + 1] = b | (c << 16);   // the pixels themselves
+            v[(dy + 1) * 3 + 2] = c | (d << 16);   // right neighbours
+        }
         // 19-exchange median-of-9 network
-        cswap(v[1], v[2]); cswap(v[4], v[5]); cswap(v[7], v[8]); cswap(v[0], v[1]); cswap(v[3], v[4]); cswap(v[6], v[7]);
-        cswap(v[1], v[2]); cswap(v[4], v[5]); cswap(v[7], v[8]); cswap(v[0], v[3]); cswap(v[5], v[8]); cswap(v[4], v[7]);
-        cswap(v[3], v[6]); cswap(v[1], v[4]); cswap(v[2], v[5]); cswap(v[4], v[7]); cswap(v[4], v[2]); cswap(v[6], v[4]);
-        cswap(v[4], v[2]);
-        o[i] = (int16_t)v[4];
+        cswap2(v[1], v[2]); cswap2(v[4], v[5]); cswap2(v[7], v[8]); cswap2(v[0], v[1]); cswap2(v[3], v[4]); cswap2(v[6], v[7]);
+        cswap2(v[1], v[2]); cswap2(v[4], v[5]); cswap2(v[7], v[8]); cswap2(v[0], v[3]); cswap2(v[5], v[8]); cswap2(v[4], v[7]);
+        cswap2(v[3], v[6]); cswap2(v[1], v[4]); cswap2(v[2], v[5]); cswap2(v[4], v[7]); cswap2(v[4], v[2]); cswap2(v[6], v[4]);
+        cswap2(v[4], v[2]);
+        o[(size_t)y * W + x] = (int16_t)(v[4] & 0xFFFFu);
+        if (x + 1 < W) o[(size_t)y * W + x + 1] = (int16_t)(v[4] >> 16);
     }
 }
 
@@ -1001,7 +1008,7 @@ int sgbm_launch(const SgbmDims& d, const SgbmWorkspace* ws0, size_t ws_stride, i
     if (rc) return rc;
     const int n = d.W * d.H;
     const size_t out_stride = (size_t)n * 2;
-    dim3 gimg(cdiv(n, 256 * kEPT), nb);
+    dim3 gimg(cdiv(((d.W + 1) / 2) * d.H, 256 * kEPT), nb);
     if (d.speckleWin <= 0) {
         OVO_LAUNCH(k_median3, gimg, dim3(256), 0, st, ws.raw, ws_stride, disp_out, out_stride, d.W, d.H);
         OVO_LAUNCH_CHECK();

@@ -260,6 +260,14 @@ static inline unsigned emu_h2(unsigned a, unsigned b, unsigned (*op)(unsigned, u
 }
 static inline unsigned __vminu2(unsigned a, unsigned b) { return emu_h2(a, b, [](unsigned x, unsigned y) { return std::min(x, y); }); }
 static inline unsigned __vmaxu2(unsigned a, unsigned b) { return emu_h2(a, b, [](unsigned x, unsigned y) { return std::max(x, y); }); }
+static inline unsigned __vmins2(unsigned a, unsigned b) {
+    const short al = (short)(a & 0xFFFF), ah = (short)(a >> 16), bl = (short)(b & 0xFFFF), bh = (short)(b >> 16);
+    return (unsigned)(unsigned short)std::min(al, bl) | ((unsigned)(unsigned short)std::min(ah, bh) << 16);
+}
+static inline unsigned __vmaxs2(unsigned a, unsigned b) {
+    const short al = (short)(a & 0xFFFF), ah = (short)(a >> 16), bl = (short)(b & 0xFFFF), bh = (short)(b >> 16);
+    return (unsigned)(unsigned short)std::max(al, bl) | ((unsigned)(unsigned short)std::max(ah, bh) << 16);
+}
 static inline unsigned __vimin3_u16x2(unsigned a, unsigned b, unsigned c) { return __vminu2(__vminu2(a, b), c); }
 static inline unsigned __vimax3_u16x2(unsigned a, unsigned b, unsigned c) { return __vmaxu2(__vmaxu2(a, b), c); }
 static inline unsigned __viaddmin_u16x2(unsigned a, unsigned b, unsigned c) {
