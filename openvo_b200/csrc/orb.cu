@@ -20,8 +20,10 @@ namespace {
 
 constexpr int kEdge = 31, kFastT = 20, kHalfPatch = 15;
 
-__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
-__constant__ signed char c_pattern[1024] = {
+// u_max of the circular patch per |v|: {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3}, packed 4 bits each below
+// global (not __constant__) memory: it is copied to shared memory with coalesced word loads; constant memory would serialise the
+// 32 different addresses of a warp
+__device__ __align__(16) const signed char c_pattern[1024] = {
 #include "orb_pattern.inc"
 };
 // 7-tap sigma=2 Gaussian, float32: k0..k3 (symmetric)
@@ -444,8 +446,9 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 __global__ void __launch_bounds__(128) k_orb_describe(OrbDims d, OrbWorkspace ws, size_t ws_stride, const int32_t* __restrict__ n_sel,
                                                       float* __restrict__ kp_out, uint8_t* __restrict__ desc_out) {
     // the sampling pattern is indexed per lane: constant memory would serialise the 32 different addresses
-    __shared__ signed char s_pattern[1024];
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_pattern[i] = c_pattern[i];
+    __shared__ __align__(16) signed char s_pattern[1024];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        reinterpret_cast<uint32_t*>(s_pattern)[i] = reinterpret_cast<const uint32_t*>(c_pattern)[i];
     __syncthreads();
     const int f = blockIdx.y;
     const int lane = threadIdx.x & 31;
@@ -462,7 +465,7 @@ __global__ void __launch_bounds__(128) k_orb_describe(OrbDims d, OrbWorkspace ws
     int m10 = 0, m01 = 0;
     if (lane < 31) {
         const int v = lane - kHalfPatch;
-        const int um = c_umax[abs(v)];
+        const int um = (int)((0x3689abcddeeeffffull >> (4 * abs(v))) & 15ull);  // c_umax[|v|], 4 bits each (a per-lane constant-memory index would serialise)
         const uint8_t* r = img + (size_t)(y0 + v) * L.w + x0;
         int rs = 0;
         for (int u = -um; u <= um; u++) {
