@@ -273,12 +273,17 @@ __device__ __forceinline__ void stv(uint32_t* p, const uint32_t (&v)[NPR]) {
 // on the other with a fresh (zero) predecessor, so every warp does exactly H steps.  Cell offsets are 32-bit word
 // offsets inside one frame's volume (< 2^32 words up to 4K / 256 disparities).
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kVertPF = 8;
+#ifndef OVO_VERT_PF4
+#define OVO_VERT_PF4 4
+#endif
+template <int NPR>
+__host__ __device__ constexpr int vert_pf() { return NPR == 4 ? OVO_VERT_PF4 : 8; }  // register prefetch depth (cells)
 
 template <int NPR, bool PAD, int DIR, bool UP>
 __device__ __forceinline__ void vert_line(const SgbmDims& d, const uint32_t* __restrict__ C, uint32_t* __restrict__ Lout, int line,
                                           int lane) {
     constexpr int WPC = 32 * NPR;  // words per cell
+    constexpr int kVertPF = vert_pf<NPR>();
     constexpr int STEP = DIR == 0 ? 1 : (DIR == 2 ? -1 : 0);
     const int W1 = d.W1, H = d.H;
     const int xreset = DIR == 0 ? 0 : (DIR == 2 ? W1 - 1 : -1);
