@@ -27,7 +27,7 @@ sys.path.insert(0, ROOT)
 CONFIGS = {
     "K": dict(W=1241, H=376, D=128, n=2000, seqs=48, name="KITTI-shaped 1241x376 stereo, ORB 2000 kp, StereoSGBM 128 disp"),
     "F": dict(W=1920, H=1080, D=256, n=5000, seqs=16, name="1920x1080 stereo, ORB 5000 kp, StereoSGBM 256 disp"),
-    "U": dict(W=3840, H=2160, D=256, n=10000, seqs=2, name="3840x2160 stereo, ORB 10000 kp, StereoSGBM 256 disp"),
+    "U": dict(W=3840, H=2160, D=256, n=10000, seqs=4, name="3840x2160 stereo, ORB 10000 kp, StereoSGBM 256 disp"),
     "S": dict(W=640, H=200, D=64, n=500, seqs=48, name="small 640x200 stereo, ORB 500 kp, StereoSGBM 64 disp (dev only)"),
 }
 N_DISTINCT = 6  # distinct rendered frames; sequences ping-pong through them with different phases
