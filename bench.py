@@ -324,7 +324,13 @@ def main():
             t = torch.tensor([ms], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return dict(ms=ms, ok=ok, h2d=(sum(e.h2d_bytes for e in engs) - h2d0) / a.steps, d2h=(sum(e.d2h_bytes for e in engs) - d2h0) / a.steps,
+        causes = {}
+        for bt in bos:
+            for b in bt:
+                for od in b.odometers:
+                    key = od.skip_cause or "none"
+                    causes[key] = causes.get(key, 0) + 1
+        return dict(ms=ms, ok=ok, causes=causes, h2d=(sum(e.h2d_bytes for e in engs) - h2d0) / a.steps, d2h=(sum(e.d2h_bytes for e in engs) - d2h0) / a.steps,
                     launches=lib.ovo_launch_count() - l0, clocks=clocks, bos=bos)
 
     dev = timed(host=False)
@@ -406,8 +412,10 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": workload, "frames_per_step": S * world, "sequences_per_gpu": S, "host_threads": NT, "batches_in_flight_per_thread": NG,
                            "sequences_per_batch": SP, "distinct_frames": N_DISTINCT,
-                           "l2_policy": "inputs+working set larger than L2: %d frames x ~0.47 GB SGBM volumes per step" % S,
-                           "frames_committed": dev["ok"]},
+                           "l2_policy": "inputs+working set larger than L2: %d frames x %.2f GB of SGBM volumes per step" % (
+                               S, dev["bos"][0][0].engine.workspace.numel() / max(1, SP) / 1e9),
+                           "frames_committed": dev["ok"], "frames": S * a.steps,
+                           "last_skip_cause_per_sequence": dev["causes"]},
                 "clocks": dev["clocks"], "gpu_launches": dev["launches"],
                 "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                         "ms_per_step": e2e["ms"] / a.steps},

@@ -127,7 +127,7 @@ int ovo_rigid_transform(ovo_ctx* ctx, const float* pts1_dev, const float* pts2_d
  * ovo_rigid_body_filter replaces rigid_body_filter + the boolean-mask indexing (ref: src/openVO/stereo_odometer.py:82-105,178-181):
  * greedy clique on the graph | ||p_i-p_j|| - ||q_i-q_j|| | < thr (float32, as numpy evaluates it), points compacted in place and
  * *count_dev updated.  ovo_outlier_filter replaces the single-pass outlier removal (ref: :189-197): relative residual under T
- * (f64 [12], rows of [R|t], e.g. the output of ovo_rigid_transform), keep residual < thr + median.  cap <= 4095. */
+ * (f64 [12], rows of [R|t], e.g. the output of ovo_rigid_transform), keep residual < thr + median.  cap <= 16383. */
 int ovo_rigid_body_filter(ovo_ctx* ctx, float* pts_prev_dev, float* pts_cur_dev, int32_t* count_dev, int cap, double thr, void* stream);
 int ovo_outlier_filter(ovo_ctx* ctx, float* pts_prev_dev, float* pts_cur_dev, int32_t* count_dev, int cap, const double* T_dev,
                        double thr, void* stream);

@@ -93,16 +93,19 @@ static int make_layout(const ovo_config* c, Layout* L) {
     SgbmDims& s = L->sg;
     s.W = c->width; s.H = c->height; s.D = p.numDisparities;
     s.Dp = s.D <= 64 ? 64 : (s.D <= 128 ? 128 : 256);
-    s.W1 = s.W - s.D; s.bs = p.blockSize; s.P1 = p.P1;
-    s.P2 = p.P2 > p.P1 + 1 ? p.P2 : p.P1 + 1;
-    s.uniq = p.uniquenessRatio;
+    // OpenCV's own normalisation of non-positive arguments (cv2.StereoSGBM_create defaults to P1 = P2 = 0): P1 <= 0 -> 2,
+    // P2 <= 0 -> 5, then P2 = max(P2, P1 + 1); uniquenessRatio < 0 -> 10
+    s.W1 = s.W - s.D; s.bs = p.blockSize; s.P1 = p.P1 > 0 ? p.P1 : 2;
+    const int p2 = p.P2 > 0 ? p.P2 : 5;
+    s.P2 = p2 > s.P1 + 1 ? p2 : s.P1 + 1;
+    s.uniq = p.uniquenessRatio >= 0 ? p.uniquenessRatio : 10;
     s.disp12 = p.disp12MaxDiff > 0 ? p.disp12MaxDiff : 1;
     s.ftzero = (p.preFilterCap > 15 ? p.preFilterCap : 15) | 1;
     s.speckleWin = p.speckleWindowSize; s.speckleDiff = 16 * p.speckleRange;
     if (c->sgbm_mode != 0 && c->sgbm_mode != 1) { set_error("sgbm_mode must be 0 (MODE_SGBM) or 1 (MODE_HH)"); return 1; }
     s.mode = c->sgbm_mode;
     if (s.ftzero > 127) { set_error("preFilterCap too large"); return 1; }
-    if (s.P1 < 0 || s.bs * s.bs * (2 * s.ftzero + 63) + s.P2 > 32767) {
+    if (s.bs * s.bs * (2 * s.ftzero + 63) + s.P2 > 32767) {
         set_error("SGBM parameters leave the int16 cost domain OpenCV's result is pinned for (SURVEY.md A.4 validity domain)");
         return 1;
     }
@@ -233,6 +236,7 @@ ovo_ctx* ovo_create(const ovo_config* cfg, void* workspace_dev, size_t workspace
         return nullptr;
     }
     ovo_ctx* c = new ovo_ctx();
+    c->h_lvl = nullptr; c->h_resp = nullptr; c->h_sel = nullptr; c->h_nsel = nullptr;
     c->cfg = *cfg; c->L = L; c->base = (uint8_t*)workspace_dev;
     sgbm_carve(L.sg, c->base, &c->sg0);
     orb_carve(L.orb, c->base + L.sgbm_bytes, &c->orb0);
@@ -253,7 +257,7 @@ ovo_ctx* ovo_create(const ovo_config* cfg, void* workspace_dev, size_t workspace
     ok = ok && cudaMallocHost((void**)&c->h_nsel, (size_t)nb * 4) == cudaSuccess;
     if (!ok) {
         set_error("ovo_create: CUDA failure while staging tables (%s)", cudaGetErrorString(cudaGetLastError()));
-        delete c;
+        ovo_destroy(c);  // frees whichever pinned buffers were allocated (the others are still null)
         return nullptr;
     }
     return c;
@@ -261,7 +265,10 @@ ovo_ctx* ovo_create(const ovo_config* cfg, void* workspace_dev, size_t workspace
 
 void ovo_destroy(ovo_ctx* c) {
     if (!c) return;
-    cudaFreeHost(c->h_lvl); cudaFreeHost(c->h_resp); cudaFreeHost(c->h_sel); cudaFreeHost(c->h_nsel);
+    if (c->h_lvl) cudaFreeHost(c->h_lvl);
+    if (c->h_resp) cudaFreeHost(c->h_resp);
+    if (c->h_sel) cudaFreeHost(c->h_sel);
+    if (c->h_nsel) cudaFreeHost(c->h_nsel);
     delete c;
 }
 

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(256) k_consistency(const float* __restrict__ p
     }
 }
 
-// block-wide argmax of key = value << 12 | (4095 - index): the largest value, ties to the lowest index (np.argmax)
+// block-wide argmax of key = value << 14 | (16383 - index): the largest value, ties to the lowest index (np.argmax)
 __device__ int block_argmax(uint32_t key, uint32_t* sh) {
     key = __reduce_max_sync(0xffffffffu, key);
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = key;
@@ -64,8 +64,8 @@ __global__ void __launch_bounds__(1024) k_clique(const uint32_t* __restrict__ bi
     const int m = min(*count, cap);
     const int words = (cap + 31) / 32;
     if (m <= 0) return;
-    // m <= 4095 (key packing); each thread owns vertices tid, tid + 1024, ...
-    constexpr int PER = 4;
+    // m <= 16383 (key packing: degree and index take 14 bits each); each thread owns vertices tid, tid + 1024, ...
+    constexpr int PER = 16;
     bool comp[PER], inq[PER];
     int deg[PER];
     for (int k = 0; k < PER; k++) {
@@ -77,14 +77,14 @@ __global__ void __launch_bounds__(1024) k_clique(const uint32_t* __restrict__ bi
         uint32_t key = 0;
         for (int k = 0; k < PER; k++) {
             const int v = threadIdx.x + 1024 * k;
-            if (v < m && (first || (comp[k] && !inq[k]))) key = max(key, ((uint32_t)deg[k] << 12) | (uint32_t)(4095 - v));
+            if (v < m && (first || (comp[k] && !inq[k]))) key = max(key, ((uint32_t)deg[k] << 14) | (uint32_t)(16383 - v));
         }
         return block_argmax(key, sh);
     };
     int key = best_of(true);
     for (int it = 0; it <= m; it++) {
         if (key == 0) break;                      // no candidate left (degrees are >= 1: every point is consistent with itself)
-        const int sel = 4095 - (key & 4095);
+        const int sel = 16383 - (key & 16383);
         for (int k = 0; k < PER; k++) {
             const int v = threadIdx.x + 1024 * k;
             if (v < m) {
@@ -187,7 +187,7 @@ size_t filter_scratch_bytes(int cap) {
 
 // prev/cur: f32 [cap][3] (compacted in place through scratch), count: device i32 (updated)
 int rigid_filter_launch(float* prev, float* cur, int32_t* count, int cap, float thr, uint8_t* scratch, cudaStream_t st) {
-    if (cap > 4095) { set_error("rigid_body_filter supports at most 4095 points"); return 1; }
+    if (cap > 16383) { set_error("rigid_body_filter supports at most 16383 points"); return 1; }
     const size_t words = (cap + 31) / 32;
     uint32_t* bits = (uint32_t*)scratch; scratch += align_up((size_t)cap * words * 4, 256);
     int32_t* degree = (int32_t*)scratch; scratch += align_up((size_t)cap * 4, 256);

@@ -78,10 +78,13 @@ def _rot_y(a):
 def make_scene(W, seed=12345):
     rng = np.random.default_rng(seed)
     f = 718.856 * (W / 1241.0)
-    planes = [dict(Z=20.0, ext=None, tex=_texture(rng), cell=20.0 / f)]
+    # one texel per pixel on every plane, so the (wrapping) texture must be wider than the image: a 2048-texel texture repeats
+    # inside a 3840-pixel frame, and the duplicated patches turn half of the 4K matches into 2048-pixel outliers
+    n = 2048 if W <= 2040 else 4096
+    planes = [dict(Z=20.0, ext=None, tex=_texture(rng, n), cell=20.0 / f)]
     for Z, cx, cy, hw, hh in ((14.0, -6.0, -0.5, 3.0, 1.6), (10.0, 4.0, 0.8, 1.8, 1.2), (7.5, -2.0, 0.6, 1.1, 0.8),
                               (6.0, 1.4, -0.4, 0.7, 0.5), (5.0, -0.9, 0.7, 0.4, 0.3), (16.0, 7.0, -2.0, 3.0, 2.0)):
-        planes.append(dict(Z=Z, ext=(cx - hw, cx + hw, cy - hh, cy + hh), tex=_texture(rng), cell=Z / f))
+        planes.append(dict(Z=Z, ext=(cx - hw, cx + hw, cy - hh, cy + hh), tex=_texture(rng, n if 2 * hw * f / Z > 2040 else 2048), cell=Z / f))
     planes.sort(key=lambda p: -p["Z"])
     return planes
 
@@ -96,14 +99,26 @@ def render(planes, W, H, R, t, noise_rng=None):
     o = -R.T @ t
     img = np.zeros((H, W), np.float32)
     for p in planes:
-        lam = (p["Z"] - o[2]) / dw[..., 2]
-        X, Y = o[0] + lam * dw[..., 0], o[1] + lam * dw[..., 1]
+        ys, xs = slice(0, H), slice(0, W)
+        if p["ext"] is not None:
+            # a bounded plane is only evaluated inside the (padded) bounding box of its projected corners: same values, less work
+            x0, x1, y0, y1 = p["ext"]
+            c = np.array([[x0, y0, p["Z"]], [x1, y0, p["Z"]], [x0, y1, p["Z"]], [x1, y1, p["Z"]]]) @ R.T + t
+            if (c[:, 2] > 1e-6).all():
+                uu, vv = f * c[:, 0] / c[:, 2] + cx, f * c[:, 1] / c[:, 2] + cy
+                xs = slice(int(np.clip(np.floor(uu.min()) - 3, 0, W)), int(np.clip(np.ceil(uu.max()) + 4, 0, W)))
+                ys = slice(int(np.clip(np.floor(vv.min()) - 3, 0, H)), int(np.clip(np.ceil(vv.max()) + 4, 0, H)))
+                if xs.start >= xs.stop or ys.start >= ys.stop:
+                    continue
+        d = dw[ys, xs]
+        lam = (p["Z"] - o[2]) / d[..., 2]
+        X, Y = o[0] + lam * d[..., 0], o[1] + lam * d[..., 1]
         hit = lam > 0
         if p["ext"] is not None:
             x0, x1, y0, y1 = p["ext"]
             hit &= (X >= x0) & (X <= x1) & (Y >= y0) & (Y <= y1)
         val = _sample(p["tex"], X / p["cell"], Y / p["cell"])
-        img = np.where(hit, val, img)
+        img[ys, xs] = np.where(hit, val, img[ys, xs])
     if noise_rng is not None:
         img = img + noise_rng.normal(0, 1.0, img.shape).astype(np.float32)
     return np.clip(np.rint(img), 0, 255).astype(np.uint8)

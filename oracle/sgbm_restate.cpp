@@ -159,8 +159,13 @@ int orc_sgbm_compute(const uint8_t* L, const uint8_t* R, int W, int H, int minDi
                      int speckleWindowSize, int speckleRange, int16_t* disp_out, int16_t* C_out, int16_t* S_out,
                      int16_t* raw_out, int16_t* med_out) {
     SgbmP p;
+    // OpenCV's own normalisation of non-positive arguments (cv2.StereoSGBM_create's defaults are P1 = P2 = 0): P1 <= 0 -> 2,
+    // P2 <= 0 -> 5, then P2 = max(P2, P1 + 1); uniquenessRatio < 0 -> 10 (pinned against cv2 in tests/test_oracle.py)
+    P1 = P1 > 0 ? P1 : 2;
+    P2 = std::max(P2 > 0 ? P2 : 5, P1 + 1);
+    uniquenessRatio = uniquenessRatio >= 0 ? uniquenessRatio : 10;
     p.W = W; p.H = H; p.D = numDisparities; p.bs = blockSize; p.P1 = P1;
-    p.P2 = std::max(P2, P1 + 1);
+    p.P2 = P2;
     p.uniq = uniquenessRatio;
     p.disp12 = disp12MaxDiff > 0 ? disp12MaxDiff : 1;
     p.ftzero = std::max(preFilterCap, 15) | 1;
@@ -270,8 +275,13 @@ int orc_sgbm_compute_mode(const uint8_t* L, const uint8_t* R, int W, int H, int 
         return orc_sgbm_compute(L, R, W, H, minDisparity, numDisparities, blockSize, P1, P2, disp12MaxDiff, preFilterCap,
                                 uniquenessRatio, speckleWindowSize, speckleRange, disp_out, nullptr, nullptr, nullptr, nullptr);
     SgbmP p;
+    // OpenCV's own normalisation of non-positive arguments (cv2.StereoSGBM_create's defaults are P1 = P2 = 0): P1 <= 0 -> 2,
+    // P2 <= 0 -> 5, then P2 = max(P2, P1 + 1); uniquenessRatio < 0 -> 10 (pinned against cv2 in tests/test_oracle.py)
+    P1 = P1 > 0 ? P1 : 2;
+    P2 = std::max(P2 > 0 ? P2 : 5, P1 + 1);
+    uniquenessRatio = uniquenessRatio >= 0 ? uniquenessRatio : 10;
     p.W = W; p.H = H; p.D = numDisparities; p.bs = blockSize; p.P1 = P1;
-    p.P2 = std::max(P2, P1 + 1);
+    p.P2 = P2;
     p.uniq = uniquenessRatio;
     p.disp12 = disp12MaxDiff > 0 ? disp12MaxDiff : 1;
     p.ftzero = std::max(preFilterCap, 15) | 1;

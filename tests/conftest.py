@@ -49,6 +49,9 @@ SGBM_CASES = [
     (320, 48, 64, dict(blockSize=3, P1=72, P2=288, uniquenessRatio=0, speckleWindowSize=0)),
     (240, 64, 48, dict(blockSize=7, preFilterCap=15, uniquenessRatio=15, disp12MaxDiff=2, speckleWindowSize=50, speckleRange=1)),
     (240, 64, 16, dict(blockSize=11, P1=100, P2=1000, disp12MaxDiff=-1)),
+    # cv2.StereoSGBM_create's own defaults: P1 = P2 = 0 (-> 2 / 5 inside OpenCV) and uniquenessRatio < 0 (-> 10)
+    (200, 60, 32, dict(P1=0, P2=0)),
+    (200, 60, 32, dict(P1=7, P2=0, uniquenessRatio=-1)),
 ]
 
 
