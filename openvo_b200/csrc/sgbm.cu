@@ -3,17 +3,31 @@
 // Replaces cv2.StereoSGBM.compute as called by the reference at src/openVO/stereo_camera.py:51 (object built at
 // :23-27).  Semantics: SURVEY.md Appendix A.4 (bit-exact; oracle = oracle/sgbm_restate.cpp).
 //
-// Data flow (per frame, all in HBM/L2; D padded to Dp in {64,128,256} so that one warp owns one cost vector):
+// Data flow (per frame, all in HBM/L2; D padded to Dp in {64,128,256}):
 //   k_sgbm_prep   images -> byte-packed (v, vmin, vmax) planes for the Sobel-x-clipped and the raw rows (A.4.1)
-//   k_sgbm_cost   prep   -> C[y][x1][d] int16 : Birchfield-Tomasi cost summed over the blockSize^2 window (A.4.2)
-//   k_sgbm_vert   C      -> Lv[3][y][x1][d]   : paths from (x-1,y-1), (x,y-1), (x+1,y-1); one warp per scan line
-//   k_sgbm_horiz  C, Lv  -> raw disparity     : paths from (x-1,y) and (x+1,y) run towards each other by two warps
+//   k_sgbm_cost   prep   -> C[y][x1][word] int16x2 : Birchfield-Tomasi cost summed over the blockSize^2 window (A.4.2)
+//   k_sgbm_vsum   C      -> Sv[y][x1][word] = sat(L1 + L2 + L3): the three top-down paths (from (x-1,y-1), (x,y-1), (x+1,y-1)) of
+//                                               a band of 16 rows x a tile of columns per CTA; a warp carries the path state of a
+//                                               few adjacent scan lines in registers and follows them through the band; the three
+//                                               directions of a cell meet in a three-row shared-memory ring (V stores, the first
+//                                               diagonal adds, the second adds and writes Sv), so only ONE volume leaves the chip.
+//                                               Diagonal lines that enter a tile from the side are recomputed from the band's top
+//                                               row (a 16-column halo); path state crosses bands through a small L2-resident buffer
+//   k_sgbm_vert   C      -> Lv[6][y][x1][word] : MODE_HH only (opt-in): one volume per direction, one warp per scan line
+//   k_sgbm_horiz  C, Sv  -> raw disparity     : paths from (x-1,y) and (x+1,y) run towards each other by two warps
 //                                               per row, parking their state every 4 cells; whoever reaches a cell
 //                                               second replays the other's path from the checkpoint, owns the complete
 //                                               5-path sum and does WTA / uniqueness / sub-pixel / disp2; then the LR check
 //   k_median3, k_ccl_*   -> 3x3 median and speckle filter (connected components, union-find)
+// Cost-vector layout ("half-split"): 32-bit word k of a cell (k < Dp/2) holds disparity k in its low and disparity k + Dp/2 in
+// its high half.  The d-1 / d+1 neighbours of a word are then simply the previous / next WORD, so the path recurrence needs
+// no funnel shifts; only the first and the last word of a vector need a byte permute (MAX_COST enters there).
 // All cost arithmetic is packed 2 x u16 per register on the DPX pipe (VIADDMNMX.U16x2 / VIMNMX.U16x2); the per-cell
 // minimum is one CREDUX.MIN.  No tensor cores: nothing here is a contraction.
+#include <cstdlib>
+#include <cstring>
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace ovo {
@@ -80,7 +94,7 @@ __global__ void __launch_bounds__(256) k_sgbm_prep(const uint8_t* __restrict__ l
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// A.4.1 + A.4.2 cost volume.  A thread owns one disparity pair (d, d+1) of one unit = (TX columns) x (RS rows); it
+// A.4.1 + A.4.2 cost volume.  A thread owns one word (disparities k and k + Dp/2) of one unit = (TX columns) x (RS rows); it
 // walks the rows of the strip, and inside a row the TX + 2*SW2 columns, keeping the horizontal window in registers
 // and the vertical window as a ring of horizontal sums in (thread-private, conflict-free) shared memory.
 // ------------------------------------------------------------------------------------------------------------
@@ -91,7 +105,7 @@ constexpr int kCostThreads = 128;
 constexpr int kCostRS = OVO_COST_RS;  // rows per unit (the vertical window adds 2*SW2 halo rows)
 
 __device__ __forceinline__ uint32_t bt_pair(uint32_t lw, uint32_t rw0, uint32_t rw1) {
-    // lw: left word at x; rw0 / rw1: right words at x-d and x-d-1
+    // lw: left word at x; rw0 / rw1: right words at x - dlo and x - dhi
     const uint32_t v = __byte_perm(rw0, rw1, 0x7430), vmin = __byte_perm(rw0, rw1, 0x7531), vmax = __byte_perm(rw0, rw1, 0x7632);
     const uint32_t u = __byte_perm(lw, 0, 0x4040), umin = __byte_perm(lw, 0, 0x4141), umax = __byte_perm(lw, 0, 0x4242);
     const uint32_t c0 = __vmaxu2(vmin, u) - __vminu2(vmax, u);  // max(0, u - vmax, vmin - u), both halves
@@ -99,22 +113,21 @@ __device__ __forceinline__ uint32_t bt_pair(uint32_t lw, uint32_t rw0, uint32_t 
     return __vminu2(c0, c1);
 }
 
-// one row of a unit: horizontal sums of TX columns, folded into the vertical ring / running sums
+// one row of a unit: horizontal sums of TX columns, folded into the vertical ring / running sums.  The thread owns word k of
+// every cell: disparities dlo = k (low half) and dhi = k + Dp/2 (high half); a padded half (d >= D) is computed from a valid
+// address and ignored downstream (the path kernels force MAX_COST there).
 template <int SW2, int TX, bool EDGE, bool PAD>
-__device__ __forceinline__ void cost_row(const uint2* __restrict__ Lrow, const uint2* __restrict__ Rrow, int x0, int d0, int D, int W1,
-                                         bool pad, uint32_t* slot, bool have_old, uint32_t (&vs)[TX]) {
+__device__ __forceinline__ void cost_row(const uint2* __restrict__ Lrow, const uint2* __restrict__ Rrow, int x0, int dlo, int dhi, int D,
+                                         int W1, bool pad, uint32_t* slot, bool have_old, uint32_t (&vs)[TX]) {
     constexpr int BS = 2 * SW2 + 1;
     uint32_t win[BS];
 #pragma unroll
     for (int i = 0; i < BS; i++) win[i] = 0;
     uint32_t hs = 0;
-    // interior tiles: all TX + 2*SW2 columns are in range, so every address is a row base plus a compile-time offset and
-    // the right-image word of disparity d+1 is the previous column's word of disparity d
+    // interior tiles: all TX + 2*SW2 columns are in range, so every address is a row base plus a compile-time offset
     const uint2* Lb = Lrow + x0 + D;
-    const uint2* Rb = Rrow + x0 + D - d0;
-    uint2 rw[2];  // right words of this and of the previous column, alternating so that no copy is needed
-    rw[0] = rw[1] = make_uint2(0, 0);
-    if (!EDGE && (!PAD || !pad)) rw[1] = __ldg(Rb - SW2 - 1);
+    const uint2* Rb0 = Rrow + x0 + D - dlo;
+    const uint2* Rb1 = Rrow + x0 + D - dhi;
 #pragma unroll
     for (int j = -SW2; j < TX + SW2; j++) {
         uint32_t pix = 0;
@@ -123,13 +136,12 @@ __device__ __forceinline__ void cost_row(const uint2* __restrict__ Lrow, const u
             if (EDGE) {
                 const int xx = min(max(x0 + j, 0), W1 - 1);
                 lw = __ldg(Lrow + xx + D);
-                r0 = __ldg(Rrow + xx + D - d0);
-                r1 = __ldg(Rrow + xx + D - d0 - 1);
+                r0 = __ldg(Rrow + xx + D - dlo);
+                r1 = __ldg(Rrow + xx + D - dhi);
             } else {
                 lw = __ldg(Lb + j);
-                rw[(j + SW2) & 1] = __ldg(Rb + j);
-                r0 = rw[(j + SW2) & 1];
-                r1 = rw[((j + SW2) & 1) ^ 1];
+                r0 = __ldg(Rb0 + j);
+                r1 = __ldg(Rb1 + j);
             }
             const uint32_t cg = bt_pair(lw.x, r0.x, r1.x);
             const uint32_t cr = bt_pair(lw.y, r0.y, r1.y);
@@ -163,8 +175,9 @@ __global__ void __launch_bounds__(kCostThreads, OVO_COST_MINB) k_sgbm_cost(SgbmD
     const int x0 = (unit % n_xt) * TX, y0 = (unit / n_xt) * kCostRS;
     const int f = blockIdx.z;
     const int W = d.W, H = d.H, D = d.D, W1 = d.W1;
-    const int d0 = 2 * threadIdx.x;
-    const bool pad = d0 >= D;
+    const int dlo = threadIdx.x;                                  // word k: disparities k and k + Dp/2
+    const bool pad = dlo >= D;                                    // both halves padded
+    const int dhi = dlo + npairs < D ? dlo + npairs : dlo;        // a padded high half reads a valid address; its value is ignored
     const uint2* prep = reinterpret_cast<const uint2*>(frame_ptr(ws.prep, ws_stride, f));
     const size_t plane = (size_t)H * W;
     uint32_t* Cw = reinterpret_cast<uint32_t*>(frame_ptr(ws.C, ws_stride, f));
@@ -181,8 +194,8 @@ __global__ void __launch_bounds__(kCostThreads, OVO_COST_MINB) k_sgbm_cost(SgbmD
         const uint2* Lrow = prep + (size_t)yc * W;
         const uint2* Rrow = Lrow + plane;
         uint32_t* slot = ring + (size_t)(k % BS) * TX * kCostThreads + tid;
-        if (edge) cost_row<SW2, TX, true, PAD>(Lrow, Rrow, x0, d0, D, W1, pad, slot, k >= BS, vs);
-        else cost_row<SW2, TX, false, PAD>(Lrow, Rrow, x0, d0, D, W1, pad, slot, k >= BS, vs);
+        if (edge) cost_row<SW2, TX, true, PAD>(Lrow, Rrow, x0, dlo, dhi, D, W1, pad, slot, k >= BS, vs);
+        else cost_row<SW2, TX, false, PAD>(Lrow, Rrow, x0, dlo, dhi, D, W1, pad, slot, k >= BS, vs);
         const int y = r - SW2;
         if (y >= y0) {
             uint32_t* out = Cw + ((size_t)y * W1 + x0) * npairs + threadIdx.x;
@@ -194,66 +207,100 @@ __global__ void __launch_bounds__(kCostThreads, OVO_COST_MINB) k_sgbm_cost(SgbmD
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// A.4.3 one path step on a warp-wide cost vector.  Lane l owns d in [2*NPR*l, 2*NPR*(l+1)), two per register.
+// A.4.3 one path step on a cost vector held by LPC lanes (LPC = 32: one cell per warp; 8 or 16: 4 or 2 adjacent cells per
+// warp), NPR words per lane: lane q of a cell owns words [q*NPR, (q+1)*NPR), word k = (disparity k | disparity k + Dp/2 << 16).
 // A predecessor outside the image is the all-zero vector with min 0, for which the step formula yields L = C, so path
 // (re)starts are just a state reset followed by the ordinary step.
 // ------------------------------------------------------------------------------------------------------------
 template <int NPR>
 struct PathState {
     uint32_t L[NPR];
-    uint32_t m;  // min over d of L (warp-uniform)
+    uint32_t mm;  // min over d of L, in both halves (uniform over the cell's lanes)
 };
 
 template <int NPR>
 __device__ __forceinline__ void path_reset(PathState<NPR>& s) {
 #pragma unroll
     for (int r = 0; r < NPR; r++) s.L[r] = 0;
-    s.m = 0;
+    s.mm = 0;
 }
 
-template <int NPR>
-__device__ __forceinline__ uint32_t vec_min(const uint32_t (&L)[NPR]) {  // min over d (warp-uniform)
+// lane-constant operands of path_step
+template <int LPC>
+struct PathLane {
+    int src_below, src_above;      // lanes holding word k-1 of my first word / word k+1 of my last word (wrapping inside the cell)
+    uint32_t sel_below, sel_above; // byte-permute selectors: identity, except at the two ends of the vector where MAX_COST enters
+    uint32_t gmask;                // the lanes of my cell
+    __device__ __forceinline__ void init(int lane) {
+        const int q = lane & (LPC - 1), base = lane & ~(LPC - 1);
+        src_below = base | ((q - 1) & (LPC - 1));
+        src_above = base | ((q + 1) & (LPC - 1));
+        // word -1 = (MAX_COST, disparity Dp/2 - 1 = low half of the last word); word Dp/2 = (disparity Dp/2 = high half of word 0, MAX_COST)
+        sel_below = q == 0 ? 0x1054u : 0x3210u;
+        sel_above = q == LPC - 1 ? 0x7632u : 0x3210u;
+        gmask = LPC == 32 ? 0xffffffffu : (((1u << (LPC & 31)) - 1u) << base);
+    }
+};
+
+template <int LPC, int NPR>
+__device__ __forceinline__ uint32_t vec_min(const uint32_t (&L)[NPR], const PathLane<LPC>& pl) {  // min over d, broadcast to both halves
     uint32_t t = L[0];
 #pragma unroll
     for (int r = 1; r < NPR; r++) t = __vminu2(t, L[r]);
-    return __reduce_min_sync(0xffffffffu, min(t & 0xFFFFu, t >> 16));
+    t = __vminu2(t, __byte_perm(t, 0, 0x1032));  // both halves = min(lo, hi): 32-bit order == 16-bit order from here on
+    if constexpr (LPC == 32) {
+        return __reduce_min_sync(0xffffffffu, t);
+    } else {
+        // several cells per warp: REDUX wants one mask for the whole warp (per-cell masks take ptxas' divergent slow path), so
+        // the cell's lanes run a butterfly instead
+#pragma unroll
+        for (int o = 1; o < LPC; o <<= 1) t = min(t, __shfl_xor_sync(0xffffffffu, t, o));
+        return t;
+    }
 }
 
-template <int NPR, bool PAD>
+template <int LPC, int NPR, bool PAD>
 __device__ __forceinline__ void path_step(PathState<NPR>& s, const uint32_t (&c)[NPR], const uint32_t (&padmask)[NPR],
-                                          uint32_t P1P1, uint32_t P2, bool lane_first, bool lane_last) {
-    uint32_t below = __shfl_up_sync(0xffffffffu, s.L[NPR - 1], 1);  // neighbour lane's top pair
-    uint32_t above = __shfl_down_sync(0xffffffffu, s.L[0], 1);      // neighbour lane's bottom pair
-    if (lane_first) below = kMaxC2;                                  // Lp[-1] = MAX_COST
-    if (lane_last) above = kMaxC2;                                   // Lp[D]  = MAX_COST
-    const uint32_t mP2 = bcast16(s.m + P2), mm = bcast16(s.m);
+                                          uint32_t P1P1, uint32_t P2P2, const PathLane<LPC>& pl) {
+    uint32_t below = __shfl_sync(0xffffffffu, s.L[NPR - 1], pl.src_below);
+    uint32_t above = __shfl_sync(0xffffffffu, s.L[0], pl.src_above);
+    below = __byte_perm(below, kMaxC2, pl.sel_below);  // Lp[-1] = MAX_COST
+    above = __byte_perm(above, kMaxC2, pl.sel_above);  // Lp[Dp] = MAX_COST
+    const uint32_t mP2 = s.mm + P2P2;
     uint32_t out[NPR];
 #pragma unroll
     for (int r = 0; r < NPR; r++) {
-        const uint32_t dm1 = __funnelshift_l(r == 0 ? below : s.L[r - 1], s.L[r], 16);       // Lp[d-1]
-        const uint32_t dp1 = __funnelshift_r(s.L[r], r == NPR - 1 ? above : s.L[r + 1], 16); // Lp[d+1]
+        const uint32_t dm1 = r == 0 ? below : s.L[r - 1];        // Lp[d-1]
+        const uint32_t dp1 = r == NPR - 1 ? above : s.L[r + 1];  // Lp[d+1]
         uint32_t t = __viaddmin_u16x2(dm1, P1P1, s.L[r]);
         t = __viaddmin_u16x2(dp1, P1P1, t);
         t = __vminu2(t, mP2);
-        out[r] = c[r] + (t - mm);
+        out[r] = c[r] + (t - s.mm);
         if (PAD) out[r] |= padmask[r];
     }
 #pragma unroll
     for (int r = 0; r < NPR; r++) s.L[r] = out[r];
-    s.m = vec_min<NPR>(s.L);
+    s.mm = vec_min<LPC, NPR>(s.L, pl);
 }
 
-template <int NPR>
+template <int LPC, int NPR>
 __device__ __forceinline__ void make_padmask(uint32_t (&padmask)[NPR], int lane, int D) {
+    const int q = lane & (LPC - 1);
 #pragma unroll
-    for (int r = 0; r < NPR; r++) padmask[r] = (2 * (NPR * lane + r) >= D) ? kMaxC2 : 0u;
+    for (int r = 0; r < NPR; r++) {
+        const int k = q * NPR + r;
+        padmask[r] = (k >= D ? 0x7FFFu : 0u) | (k + LPC * NPR >= D ? 0x7FFF0000u : 0u);
+    }
 }
 
 template <int NPR>
 __device__ __forceinline__ void ldv(uint32_t (&v)[NPR], const uint32_t* p) {
-    if constexpr (NPR == 4) {
-        const uint4 t = *reinterpret_cast<const uint4*>(p);
-        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    if constexpr (NPR % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < NPR; i += 4) {
+            const uint4 t = *reinterpret_cast<const uint4*>(p + i);
+            v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+        }
     } else if constexpr (NPR == 2) {
         const uint2 t = *reinterpret_cast<const uint2*>(p);
         v[0] = t.x; v[1] = t.y;
@@ -263,9 +310,14 @@ __device__ __forceinline__ void ldv(uint32_t (&v)[NPR], const uint32_t* p) {
 }
 template <int NPR>
 __device__ __forceinline__ void stv(uint32_t* p, const uint32_t (&v)[NPR]) {
-    if constexpr (NPR == 4) *reinterpret_cast<uint4*>(p) = make_uint4(v[0], v[1], v[2], v[3]);
-    else if constexpr (NPR == 2) *reinterpret_cast<uint2*>(p) = make_uint2(v[0], v[1]);
-    else *p = v[0];
+    if constexpr (NPR % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < NPR; i += 4) *reinterpret_cast<uint4*>(p + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    } else if constexpr (NPR == 2) {
+        *reinterpret_cast<uint2*>(p) = make_uint2(v[0], v[1]);
+    } else {
+        *p = v[0];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -299,9 +351,10 @@ __device__ __forceinline__ void vert_line(const SgbmDims& d, const uint32_t* __r
         }
     };
     uint32_t padmask[NPR];
-    make_padmask<NPR>(padmask, lane, d.D);
-    const uint32_t P1P1 = bcast16(d.P1), P2 = d.P2;
-    const bool lane_first = lane == 0, lane_last = lane == 31;
+    make_padmask<32, NPR>(padmask, lane, d.D);
+    const uint32_t P1P1 = bcast16(d.P1), P2P2 = bcast16(d.P2);
+    PathLane<32> plane;
+    plane.init(lane);
 
     uint32_t cbuf[kVertPF][NPR];
     int xpf = line, x = line;
@@ -328,7 +381,7 @@ __device__ __forceinline__ void vert_line(const SgbmDims& d, const uint32_t* __r
                 for (int r = 0; r < NPR; r++) c[r] = cbuf[i][r];
                 ldv<NPR>(cbuf[i], ppf);
                 ppf += adv;
-                path_step<NPR, PAD>(s, c, padmask, P1P1, P2, lane_first, lane_last);
+                path_step<32, NPR, PAD>(s, c, padmask, P1P1, P2P2, plane);
                 stv<NPR>(pl, s.L);
                 pl += adv;
             }
@@ -343,7 +396,7 @@ __device__ __forceinline__ void vert_line(const SgbmDims& d, const uint32_t* __r
                 ldv<NPR>(cbuf[i], ppf);
                 next_row(xpf, ppf);
                 if (STEP != 0 && x == xreset) path_reset<NPR>(s);
-                path_step<NPR, PAD>(s, c, padmask, P1P1, P2, lane_first, lane_last);
+                path_step<32, NPR, PAD>(s, c, padmask, P1P1, P2P2, plane);
                 stv<NPR>(pl, s.L);
                 next_row(x, pl);
             }
@@ -359,7 +412,7 @@ __device__ __forceinline__ void vert_line(const SgbmDims& d, const uint32_t* __r
                 if (y + i + kVertPF < H) ldv<NPR>(cbuf[i], ppf);
                 next_row(xpf, ppf);
                 if (STEP != 0 && x == xreset) path_reset<NPR>(s);
-                path_step<NPR, PAD>(s, c, padmask, P1P1, P2, lane_first, lane_last);
+                path_step<32, NPR, PAD>(s, c, padmask, P1P1, P2P2, plane);
                 stv<NPR>(pl, s.L);
                 next_row(x, pl);
             }
@@ -387,6 +440,270 @@ __global__ void __launch_bounds__(256) k_sgbm_vert(SgbmDims d, SgbmWorkspace ws,
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Sv = sat(L1 + L2 + L3) for a band of BR rows x a tile of B columns per CTA (MODE_SGBM).  A "line group" is CPW = 32 / LPC
+// adjacent scan lines of one direction carried by one warp (LPC lanes per cell, NPR words per lane): V groups stay on their
+// columns, D1 groups (path from (x-1, y-1)) move one column to the right per row, D3 groups (from (x+1, y-1)) one to the left.
+// A tile has 16 V groups (B = 16 * CPW columns) and 16 + BR / CPW groups per diagonal direction: the extra ones start in the
+// BR columns beside the tile and are only there to carry the state of the lines that enter the tile further down (the halo is
+// recomputed instead of exchanged between CTAs, so a band is ONE launch without inter-CTA synchronisation).  Every warp owns two
+// groups.  Rows are software-pipelined over a three-row shared-memory ring: in iteration t the V groups store L2 of row t, the
+// D1 groups add L1 to row t-1 and the D3 groups add L3 to row t-2 and write the finished sum to Sv; one barrier per iteration.
+// The state of the lines at the last row of the band goes to a small buffer (3 x W1 vectors per frame and parity) from which
+// the next band's launch starts, so path state never leaves registers inside a band and Sv is the only volume written.
+// ------------------------------------------------------------------------------------------------------------
+template <int LPC>
+__host__ __device__ constexpr int vs_cpw() { return 32 / LPC; }
+// VG: V groups per tile (tile width B = VG * CPW columns); BR: rows per band = columns of halo on each side
+template <int LPC, int VG>
+__host__ __device__ constexpr int vs_tile() { return VG * vs_cpw<LPC>(); }
+template <int LPC, int BR, int VG>
+__host__ __device__ constexpr int vs_diag_groups() { return VG + BR / vs_cpw<LPC>(); }
+template <int LPC, int BR, int VG>
+__host__ __device__ constexpr int vs_warps() { return (VG + 2 * vs_diag_groups<LPC, BR, VG>()) / 2; }
+#ifndef OVO_VS_MINB
+#define OVO_VS_MINB 2
+#endif
+template <int LPC, int BR, int VG>
+__host__ __device__ constexpr int vs_ctas_per_sm() { return vs_warps<LPC, BR, VG>() <= 16 ? OVO_VS_MINB : 1; }
+
+// ---- bulk-copy (TMA 1-D) + mbarrier helpers: the C strip of a row is brought into shared memory by the copy engine ----
+#ifndef OVO_EMU
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    // bounded spin: a lost transaction traps instead of hanging the device
+#pragma unroll 1
+    for (int spin = 0; spin < (1 << 26); spin++) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(phase)
+            : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+#endif
+
+constexpr int kVsRing = 3;    // rows of the shared-memory ring in which the three directions of a cell meet
+constexpr int kVsStrips = 5;  // C strips in shared memory: rows t-2 .. t in use, rows t+1 and t+2 in flight
+
+template <int NPR>
+struct VsSlot {
+    PathState<NPR> s;
+    int kind;       // 0 = V, 1 = D1, 2 = D3 (also the pipeline delay in rows)
+    int dcol;       // words the slot's cell moves along a row of the strip / ring per image row: dx * DH
+    int scol;       // word offset of this lane's words inside a strip row: (x - (x0 - BR)) * DH + q * NPR
+    int sbase;      // word offset of the current row's strip:  (r % kVsStrips) * SW * DH
+    int rbase;      // word offset of the current row in the ring: (r % kVsRing) * B * DH
+    int32_t off;    // word offset of this lane's words in Sv for the current row (a frame's volume is < 2^31 words)
+    int32_t step;   // ... and its increment per row: (W1 + dx) * DH
+};
+
+// shared-memory position (in words) of chunk i (4 words) of lane q inside a cell of the ring: for a fixed i the lanes of a cell
+// hit consecutive 16-byte chunks (conflict-free 128-bit accesses)
+template <int LPC>
+__device__ __forceinline__ int vs_chunk(int q, int i) { return (i * LPC + q) * 4; }
+
+// The three directions of a cell meet in the ring: V stores, D1 adds, D3 adds and writes the sum to Sv.
+template <int LPC, int NPR, int BR>
+__device__ __forceinline__ void vs_meet(const VsSlot<NPR>& sl, int q, uint32_t* ring, uint32_t* __restrict__ Sv) {
+    constexpr int DH = LPC * NPR;
+    uint32_t* cell = ring + sl.rbase + (sl.scol - (BR * DH + q * NPR));
+    if (sl.kind == 0) {
+#pragma unroll
+        for (int i = 0; i < NPR / 4; i++)
+            *reinterpret_cast<uint4*>(cell + vs_chunk<LPC>(q, i)) = make_uint4(sl.s.L[4 * i], sl.s.L[4 * i + 1], sl.s.L[4 * i + 2], sl.s.L[4 * i + 3]);
+    } else {
+        uint32_t a[NPR];
+#pragma unroll
+        for (int i = 0; i < NPR / 4; i++) {
+            const uint4 v = *reinterpret_cast<const uint4*>(cell + vs_chunk<LPC>(q, i));
+            a[4 * i] = v.x; a[4 * i + 1] = v.y; a[4 * i + 2] = v.z; a[4 * i + 3] = v.w;
+        }
+#pragma unroll
+        for (int k = 0; k < NPR; k++) a[k] = __viaddmin_u16x2(a[k], sl.s.L[k], kMaxC2);
+        if (sl.kind == 1) {
+#pragma unroll
+            for (int i = 0; i < NPR / 4; i++)
+                *reinterpret_cast<uint4*>(cell + vs_chunk<LPC>(q, i)) = make_uint4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
+        } else {
+            stv<NPR>(Sv + sl.off, a);
+        }
+    }
+}
+
+template <int LPC, int NPR, int BR, int VG>
+__device__ __forceinline__ void vs_advance(VsSlot<NPR>& sl) {
+    constexpr int B = vs_tile<LPC, VG>(), DH = LPC * NPR, SW = B + 2 * BR;
+    sl.scol += sl.dcol;
+    sl.off += sl.step;
+    sl.sbase = sl.sbase == (kVsStrips - 1) * SW * DH ? 0 : sl.sbase + SW * DH;
+    sl.rbase = sl.rbase == (kVsRing - 1) * B * DH ? 0 : sl.rbase + B * DH;
+}
+
+template <int LPC, int NPR, bool PAD, int BR, int VG>
+__global__ void __launch_bounds__(32 * vs_warps<LPC, BR, VG>(), vs_ctas_per_sm<LPC, BR, VG>())
+    k_sgbm_vsum(SgbmDims d, SgbmWorkspace ws, size_t ws_stride, int y0, int parity) {
+    constexpr int CPW = vs_cpw<LPC>(), B = vs_tile<LPC, VG>(), DH = LPC * NPR, NDG = vs_diag_groups<LPC, BR, VG>(), NWARP = vs_warps<LPC, BR, VG>();
+    constexpr int SW = B + 2 * BR;  // cells of a C strip: the tile and the halo on both sides
+    static_assert(NPR % 4 == 0, "128-bit accesses");
+    OVO_DYN_SMEM(uint32_t, smem);
+    uint32_t* strips = smem;                           // [kVsStrips][SW][DH]  (first: the bulk copies want 16-byte alignment)
+    uint32_t* ring = smem + kVsStrips * SW * DH;       // [kVsRing][B][DH]
+#ifndef OVO_EMU
+    uint64_t* bar = reinterpret_cast<uint64_t*>(ring + kVsRing * B * DH);  // [kVsStrips]
+#endif
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int q = lane & (LPC - 1), g = lane / LPC;
+    const int f = blockIdx.y, x0 = blockIdx.x * B;
+    const int W1 = d.W1, H = d.H;
+    const int R = min(BR, H - y0);
+    const size_t vol = (size_t)H * W1 * DH;  // words
+    const uint32_t* __restrict__ C = reinterpret_cast<const uint32_t*>(frame_ptr(ws.C, ws_stride, f));
+    uint32_t* Sv = reinterpret_cast<uint32_t*>(frame_ptr(ws.Lv, ws_stride, f));
+    uint32_t* bb = Sv + vol;  // band-state buffer [2 parity][3 kinds][W1][DH], in the space of the second volume
+    const uint32_t* bb_in = bb + (size_t)(parity ^ 1) * 3 * W1 * DH;
+    uint32_t* bb_out = bb + (size_t)parity * 3 * W1 * DH;
+    // strip of band row rn: cells [x0 - BR, x0 + B + BR) of image row y0 + rn (running over the row ends into the neighbouring
+    // rows; the frame's workspace surrounds C, so the source is always valid memory, and those cells are never stored)
+    const uint32_t* strip_src = C + ((ptrdiff_t)y0 * W1 + (x0 - BR)) * DH;
+    auto fetch = [&](int rn) {
+        if (rn >= R) return;
+        const uint32_t* src = strip_src + (ptrdiff_t)rn * W1 * DH;
+        uint32_t* dst = strips + (rn % kVsStrips) * SW * DH;
+#ifndef OVO_EMU
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&bar[rn % kVsStrips], SW * DH * 4);
+            bulk_g2s(dst, src, SW * DH * 4, &bar[rn % kVsStrips]);
+        }
+#else
+        for (int i = threadIdx.x; i < SW * DH; i += blockDim.x) dst[i] = src[i];
+#endif
+    };
+#ifndef OVO_EMU
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < kVsStrips; i++) mbar_init(&bar[i], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+#endif
+    fetch(0);
+    fetch(1);
+
+    uint32_t padmask[NPR];
+    make_padmask<LPC, NPR>(padmask, lane, d.D);
+    const uint32_t P1P1 = bcast16(d.P1), P2P2 = bcast16(d.P2);
+    PathLane<LPC> pl;
+    pl.init(lane);
+
+    VsSlot<NPR> sl[2];
+    int x[2];  // column of this lane's cell at the band's first row
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int gid = wid + k * NWARP;
+        int xs, dx;
+        if (gid < VG) { sl[k].kind = 0; dx = 0; xs = x0 + gid * CPW; }
+        else if (gid < VG + NDG) { sl[k].kind = 1; dx = 1; xs = x0 - BR + (gid - VG) * CPW; }
+        else { sl[k].kind = 2; dx = -1; xs = x0 + (gid - VG - NDG) * CPW; }
+        x[k] = xs + g;
+        sl[k].dcol = dx * DH;
+        sl[k].scol = (x[k] - (x0 - BR)) * DH + q * NPR;
+        sl[k].sbase = 0;
+        sl[k].rbase = 0;
+        sl[k].off = (int32_t)(((ptrdiff_t)y0 * W1 + x[k]) * DH + q * NPR);
+        sl[k].step = (W1 + dx) * DH;
+        // state of the predecessor cell (x - dx, y0 - 1), or the all-zero vector when it lies outside the image
+        const int xp = x[k] - dx;
+        const bool have = y0 > 0 && xp >= 0 && xp < W1;
+        uint32_t v[NPR];
+#pragma unroll
+        for (int r = 0; r < NPR; r++) v[r] = 0;
+        if (have) ldv<NPR>(v, bb_in + ((size_t)sl[k].kind * W1 + xp) * DH + q * NPR);
+#pragma unroll
+        for (int r = 0; r < NPR; r++) sl[k].s.L[r] = v[r];
+        sl[k].s.mm = vec_min<LPC, NPR>(sl[k].s.L, pl);
+    }
+    const bool edge = x0 - BR <= 0 || x0 + B + BR >= W1;  // diagonal lines of this tile can start at the image border
+#ifdef OVO_EMU
+    __syncthreads();
+#endif
+    const int mine_lo = BR * DH + q * NPR;  // scol of the tile's first column for this lane
+
+    // iteration t: slot k computes row t - kind; the strip of row t + 2 is requested, that of row t must have landed.
+    // CHECK: some slot may be outside the band or on its last row (state hand-over); EDGE: the tile touches the image border
+    // (diagonal lines start there; cells beyond the border are computed on whatever the strip holds and never stored).
+    // The plain variant is straight-line for both slots, so that the two recurrences interleave.
+    auto iteration = [&](int t, auto check, auto edge_t) {
+        constexpr bool CHECK = decltype(check)::value, EDGE = decltype(edge_t)::value;
+        fetch(t + 2);
+#ifndef OVO_EMU
+        if (t < R) mbar_wait(&bar[t % kVsStrips], (t / kVsStrips) & 1);
+#endif
+        bool act[2], mine[2];
+        uint32_t c[2][NPR];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int r = t - sl[k].kind;
+            act[k] = !CHECK || (r >= 0 && r < R);
+            if (act[k]) ldv<NPR>(c[k], strips + sl[k].sbase + sl[k].scol);
+        }
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            if (!act[k]) continue;
+            mine[k] = (unsigned)(sl[k].scol - mine_lo) < (unsigned)(B * DH);
+            if (EDGE) {
+                const int xc = x[k] + (sl[k].dcol / DH) * (t - sl[k].kind);
+                // a diagonal line enters the image here: its predecessor lies outside (all-zero vector)
+                if (sl[k].dcol != 0 && xc == (sl[k].dcol > 0 ? 0 : W1 - 1)) path_reset<NPR>(sl[k].s);
+                mine[k] = mine[k] && xc < W1;
+            }
+            path_step<LPC, NPR, PAD>(sl[k].s, c[k], padmask, P1P1, P2P2, pl);
+        }
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            if (!act[k]) continue;
+            if (mine[k]) {
+                vs_meet<LPC, NPR, BR>(sl[k], q, ring, Sv);
+                if (CHECK && t - sl[k].kind == R - 1) {
+                    const int xc = x[k] + (sl[k].dcol / DH) * (R - 1);
+                    stv<NPR>(bb_out + ((size_t)sl[k].kind * W1 + xc) * DH + q * NPR, sl[k].s.L);
+                }
+            }
+            vs_advance<LPC, NPR, BR, VG>(sl[k]);
+        }
+        __syncthreads();
+    };
+    using T = std::true_type;
+    using F = std::false_type;
+    int t = 0;
+    if (edge) {
+        for (; t < R + 2; t++) iteration(t, T(), T());
+    } else {
+        for (; t < 2 && t < R + 2; t++) iteration(t, T(), F());
+        for (; t < R - 1; t++) iteration(t, F(), F());  // rows 2 .. R-2: every slot is inside the band and away from its last row
+        for (; t < R + 2; t++) iteration(t, T(), F());
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Paths 0 and 4 + selection (A.4.4) + LR check (A.4.5).  One CTA (two warps) per row.  Warp 0 runs path 0 left -> right,
 // warp 1 runs path 4 right -> left.  Phase 1: each warp advances its own path over its half of the row reading only C
 // and parks its state every K cells (a checkpoint, 1/K of a volume).  Phase 2: each warp continues into the other
@@ -401,9 +718,10 @@ __global__ void __launch_bounds__(256) k_sgbm_vert(SgbmDims d, SgbmWorkspace ws,
 template <int NPR>
 __host__ __device__ constexpr int horiz_seg() { return 4; }  // K: cells per checkpoint segment (= cells per batched selection)
 
+// value and disparity of half h of this lane's word r (one cell per warp): word k = lane*NPR + r, d = k + h * Dp/2
 template <int NPR>
-__device__ __forceinline__ uint32_t half_of(const uint32_t (&S)[NPR], int k) {  // k = 2*r + h, compile-time after unrolling
-    return (k & 1) ? (S[k >> 1] >> 16) : (S[k >> 1] & 0xFFFFu);
+__device__ __forceinline__ uint32_t half_of(const uint32_t (&S)[NPR], int r, int h) {
+    return h ? (S[r] >> 16) : (S[r] & 0xFFFFu);
 }
 
 // Per-cell selection, serial part only: argmin, the runner-up over |d-best| > 1 (for the uniqueness test) and the two
@@ -412,41 +730,52 @@ __device__ __forceinline__ uint32_t half_of(const uint32_t (&S)[NPR], int k) {  
 template <int NPR, bool PAD>
 __device__ __forceinline__ void wta_cell(const uint32_t (&S)[NPR], int lane, const SgbmDims& d, int x1, uint32_t* selA,
                                          uint32_t* selB, uint16_t* selBest) {
+    constexpr int DH = 32 * NPR;
     const int D = d.D;
-    const int dd0 = 2 * NPR * lane;
+    const int k0 = NPR * lane;
     // first d minimising S: the smallest (S << 9 | d)
     uint32_t kbest = 0xFFFFFFFFu;
 #pragma unroll
-    for (int k = 0; k < 2 * NPR; k++) {
-        const uint32_t key = half_of<NPR>(S, k) * 512u + (uint32_t)(dd0 + k);
-        if (!PAD || dd0 + k < D) kbest = min(kbest, key);
-    }
+    for (int r = 0; r < NPR; r++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int dd = k0 + r + h * DH;
+            const uint32_t key = half_of<NPR>(S, r, h) * 512u + (uint32_t)dd;
+            if (!PAD || dd < D) kbest = min(kbest, key);
+        }
     const uint32_t kmin = __reduce_min_sync(0xffffffffu, kbest);
     const int minS = (int)(kmin >> 9), best = (int)(kmin & 511u);
     const int fac = 100 - d.uniq;
     uint32_t m2 = 0xFFFFu;
     if (fac > 0) {  // exists d, |d-best|>1, S[d]*fac < minS*100  <=>  (min over those d) * fac < minS*100
 #pragma unroll
-        for (int k = 0; k < 2 * NPR; k++) {
-            const bool far = (uint32_t)(dd0 + k - best + 1) > 2u && (!PAD || dd0 + k < D);
-            m2 = min(m2, far ? half_of<NPR>(S, k) : 0xFFFFu);
-        }
+        for (int r = 0; r < NPR; r++)
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int dd = k0 + r + h * DH;
+                const bool far = (uint32_t)(dd - best + 1) > 2u && (!PAD || dd < D);
+                m2 = min(m2, far ? half_of<NPR>(S, r, h) : 0xFFFFu);
+            }
         m2 = __reduce_min_sync(0xffffffffu, m2);
     } else {        // uniquenessRatio >= 100: evaluate the predicate as written; park 0 = reject, 0xFFFF = accept
         bool bad = false;
 #pragma unroll
-        for (int k = 0; k < 2 * NPR; k++)
-            if ((!PAD || dd0 + k < D) && (int)half_of<NPR>(S, k) * fac < minS * 100 && abs(dd0 + k - best) > 1) bad = true;
+        for (int r = 0; r < NPR; r++)
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int dd = k0 + r + h * DH;
+                if ((!PAD || dd < D) && (int)half_of<NPR>(S, r, h) * fac < minS * 100 && abs(dd - best) > 1) bad = true;
+            }
         m2 = __any_sync(0xffffffffu, bad) ? 0u : 0xFFFFu;
     }
     auto at = [&](int dd) -> uint32_t {  // S[dd], dd warp-uniform
-        const int r = (dd % (2 * NPR)) >> 1;
+        const int k = dd % DH, r = k % NPR;
         uint32_t w = S[0];
 #pragma unroll
         for (int rr = 1; rr < NPR; rr++)
             if (r == rr) w = S[rr];
-        w = __shfl_sync(0xffffffffu, w, dd / (2 * NPR));
-        return (dd & 1) ? (w >> 16) : (w & 0xFFFFu);
+        w = __shfl_sync(0xffffffffu, w, k / NPR);
+        return dd >= DH ? (w >> 16) : (w & 0xFFFFu);
     };
     const uint32_t sm1 = at(max(best - 1, 0)), sp1 = at(min(best + 1, D - 1));
     if (lane == 0) {
@@ -457,13 +786,13 @@ __device__ __forceinline__ void wta_cell(const uint32_t (&S)[NPR], int lane, con
 }
 
 // Selection for the K = 4 cells of a segment at once (uniquenessRatio < 100, the usual case).  The warp has parked the
-// four S vectors in shared memory; 8 lanes share a cell, each scanning Dp/8 consecutive disparities, so the reductions,
-// the neighbour look-ups and the stores are paid once per four cells.  Padded disparities hold MAX_COST and the larger
-// d, so they can neither win the argmin nor lower the runner-up.
+// four S vectors in shared memory; 8 lanes share a cell, each scanning Dp/16 consecutive words (= that many disparities of the
+// lower and of the upper half of the range), so the reductions, the neighbour look-ups and the stores are paid once per four
+// cells.  Padded disparities hold MAX_COST and the larger d, so they can neither win the argmin nor lower the runner-up.
 template <int NPR>
 __device__ __forceinline__ void wta_batch(const uint32_t* svec, int lane, const SgbmDims& d, int xo, int dirx, int cnt, uint32_t* selA,
                                           uint32_t* selB, uint16_t* selBest) {
-    constexpr int WPC = 32 * NPR, NW = 4 * NPR;  // words per cell, words per lane
+    constexpr int WPC = 32 * NPR, NW = 4 * NPR;  // words per cell (= Dp/2), words per lane
     const int g = lane >> 3, q = lane & 7;
     uint32_t w[NW];
 #pragma unroll
@@ -471,31 +800,35 @@ __device__ __forceinline__ void wta_batch(const uint32_t* svec, int lane, const 
         const uint4 t = *reinterpret_cast<const uint4*>(svec + g * WPC + q * NW + i);
         w[i] = t.x; w[i + 1] = t.y; w[i + 2] = t.z; w[i + 3] = t.w;
     }
-    // first d minimising S: the smallest (S << 9 | d)
+    // first d minimising S: the smallest (S << 9 | d); word q*NW + i holds d = q*NW + i and d + WPC
     uint32_t kbest = 0xFFFFFFFFu;
 #pragma unroll
     for (int i = 0; i < NW; i++) {
-        kbest = min(kbest, (w[i] & 0xFFFFu) * 512u + (uint32_t)(2 * i));
-        kbest = min(kbest, (w[i] >> 16) * 512u + (uint32_t)(2 * i + 1));
+        kbest = min(kbest, (w[i] & 0xFFFFu) * 512u + (uint32_t)i);
+        kbest = min(kbest, (w[i] >> 16) * 512u + (uint32_t)(i + WPC));
     }
-    kbest += (uint32_t)(q * 2 * NW);
+    kbest += (uint32_t)(q * NW);
 #pragma unroll
     for (int o = 1; o < 8; o <<= 1) kbest = min(kbest, __shfl_xor_sync(0xffffffffu, kbest, o));
     const int minS = (int)(kbest >> 9), best = (int)(kbest & 511u);
-    // runner-up over |d - best| > 1: bit c of `near` marks this lane's c-th disparity as one of best-1, best, best+1
-    const uint32_t sh = (uint32_t)(best - q * 2 * NW + 1);  // bit of best+1, plus 2; huge (wrapped) when best lies far below
-    const uint32_t near = sh < 34u ? (uint32_t)((7ull << sh) >> 2) : 0u;  // 64-bit: a lane covers up to 32 disparities
+    // runner-up over |d - best| > 1: bit i of near_lo / near_hi marks the low / high half of this lane's word i as one of
+    // best-1, best, best+1
+    const uint32_t sl = (uint32_t)(best - q * NW + 1);        // bit of best+1 among the low halves, plus 2; huge (wrapped) when far below
+    const uint32_t shh = (uint32_t)(best - WPC - q * NW + 1);  // the same among the high halves
+    const uint32_t near_lo = sl < (uint32_t)(NW + 2) ? (uint32_t)((7u << sl) >> 2) : 0u;
+    const uint32_t near_hi = shh < (uint32_t)(NW + 2) ? (uint32_t)((7u << shh) >> 2) : 0u;
     uint32_t m2 = 0xFFFFu;
 #pragma unroll
     for (int i = 0; i < NW; i++) {
-        if (!(near & (1u << (2 * i)))) m2 = min(m2, w[i] & 0xFFFFu);
-        if (!(near & (1u << (2 * i + 1)))) m2 = min(m2, w[i] >> 16);
+        if (!(near_lo & (1u << i))) m2 = min(m2, w[i] & 0xFFFFu);
+        if (!(near_hi & (1u << i))) m2 = min(m2, w[i] >> 16);
     }
 #pragma unroll
     for (int o = 1; o < 8; o <<= 1) m2 = min(m2, __shfl_xor_sync(0xffffffffu, m2, o));
     if (q == 0 && g < cnt) {
         const uint16_t* sh16 = reinterpret_cast<const uint16_t*>(svec + g * WPC);
-        const uint32_t sm1 = sh16[max(best - 1, 0)], sp1 = sh16[min(best + 1, 2 * WPC - 1)];  // only used when 0 < best < D-1
+        auto at = [&](int dd) -> uint32_t { return sh16[2 * (dd % WPC) + dd / WPC]; };
+        const uint32_t sm1 = at(max(best - 1, 0)), sp1 = at(min(best + 1, 2 * WPC - 1));  // only used when 0 < best < D-1
         const int x1 = xo - dirx * g;
         selA[x1] = (uint32_t)minS | (m2 << 16);
         selB[x1] = sm1 | (sp1 << 16);
@@ -524,9 +857,10 @@ __device__ __forceinline__ void horiz_phase1(const SgbmDims& d, const HorizRow<N
     constexpr int WPC = 32 * NPR, K = horiz_seg<NPR>(), DS = DIRX * WPC;
     constexpr int PF = OVO_HOR_PF1 * K;  // register prefetch depth (cells): this phase is light, so it needs a long run-ahead
     uint32_t padmask[NPR];
-    make_padmask<NPR>(padmask, lane, d.D);
-    const uint32_t P1P1 = bcast16(d.P1), P2 = d.P2;
-    const bool lane_first = lane == 0, lane_last = lane == 31;
+    make_padmask<32, NPR>(padmask, lane, d.D);
+    const uint32_t P1P1 = bcast16(d.P1), P2P2 = bcast16(d.P2);
+    PathLane<32> pl;
+    pl.init(lane);
     const int n1 = R.n1;
     uint32_t cb[PF][NPR];
     const uint32_t* pc = R.C + (ptrdiff_t)R.xa * WPC;
@@ -547,7 +881,7 @@ __device__ __forceinline__ void horiz_phase1(const SgbmDims& d, const HorizRow<N
 #pragma unroll
                 for (int r = 0; r < NPR; r++) c[r] = cb[i][r];
                 ldv<NPR>(cb[i], pc + i * DS);
-                path_step<NPR, PAD>(s, c, padmask, P1P1, P2, lane_first, lane_last);
+                path_step<32, NPR, PAD>(s, c, padmask, P1P1, P2P2, pl);
             }
         } else {
 #pragma unroll
@@ -561,36 +895,39 @@ __device__ __forceinline__ void horiz_phase1(const SgbmDims& d, const HorizRow<N
 #pragma unroll
                     for (int r = 0; r < NPR; r++) c[r] = cb[i][r];
                     if (k + i + PF < n1) ldv<NPR>(cb[i], pc + i * DS);
-                    path_step<NPR, PAD>(s, c, padmask, P1P1, P2, lane_first, lane_last);
+                    path_step<32, NPR, PAD>(s, c, padmask, P1P1, P2P2, pl);
                 }
             }
         }
     }
 }
 
-template <int NPR, int DIRX, bool FULL>
-__device__ __forceinline__ void horiz_load_lv(const HorizRow<NPR>& R, ptrdiff_t o0, int cnt, uint32_t (&lv)[3][horiz_seg<NPR>()][NPR]) {
+// NV: volumes of vertical paths the row sums up: 1 = Sv (already L1 + L2 + L3, k_sgbm_vsum), 3 = Lv[0..2], 6 = MODE_HH
+template <int NV>
+__host__ __device__ constexpr int horiz_nreg() { return NV < 3 ? NV : 3; }  // volumes prefetched one segment ahead
+
+template <int NPR, int NV, int DIRX, bool FULL>
+__device__ __forceinline__ void horiz_load_lv(const HorizRow<NPR>& R, ptrdiff_t o0, int cnt,
+                                              uint32_t (&lv)[horiz_nreg<NV>()][horiz_seg<NPR>()][NPR]) {
     constexpr int WPC = 32 * NPR, K = horiz_seg<NPR>(), DS = DIRX * WPC;
 #pragma unroll
     for (int i = K - 1; i >= 0; i--) {  // the cell consumed first is requested first
         if (FULL || i < cnt) {
-            ldv<NPR>(lv[0][i], R.Lv + o0 - i * DS);
-            ldv<NPR>(lv[1][i], R.Lv + R.vol + o0 - i * DS);
-            ldv<NPR>(lv[2][i], R.Lv + 2 * R.vol + o0 - i * DS);
+#pragma unroll
+            for (int v = 0; v < horiz_nreg<NV>(); v++) ldv<NPR>(lv[v][i], R.Lv + v * R.vol + o0 - i * DS);
         }
     }
 }
 
-// One K-cell segment of phase 2.  On entry cb / ckv / lv hold C, the other warp's checkpoint and Lv[0..2] of segment j
-// (requested one segment earlier); on exit they hold those of segment j-1.  FULL: all K cells exist (only the segment
-// next to the rendezvous can be short).
-template <int NPR, bool PAD, bool HH, bool BATCH, int DIRX, bool FULL>
+// One K-cell segment of phase 2.  On entry cb / ckv / lv hold C, the other warp's checkpoint and the vertical sums of
+// segment j (requested one segment earlier); on exit they hold those of segment j-1.  FULL: all K cells exist (only the
+// segment next to the rendezvous can be short).
+template <int NPR, bool PAD, int NV, bool BATCH, int DIRX, bool FULL>
 __device__ __forceinline__ void horiz_segment(const SgbmDims& d, const HorizRow<NPR>& R, PathState<NPR>& s, int lane, int j, int cnt,
                                               uint32_t (&cb)[horiz_seg<NPR>()][NPR], uint32_t (&ckv)[NPR],
-                                              uint32_t (&lv)[3][horiz_seg<NPR>()][NPR], const uint32_t (&padmask)[NPR],
-                                              uint32_t P1P1, uint32_t P2) {
+                                              uint32_t (&lv)[horiz_nreg<NV>()][horiz_seg<NPR>()][NPR], const uint32_t (&padmask)[NPR],
+                                              uint32_t P1P1, uint32_t P2P2, const PathLane<32>& pl) {
     constexpr int WPC = 32 * NPR, K = horiz_seg<NPR>(), DS = DIRX * WPC;
-    const bool lane_first = lane == 0, lane_last = lane == 31;
     constexpr bool batched = BATCH;  // selection of the K cells at once; the odd uniquenessRatio >= 100 goes cell by cell
     // the other warp's cell k (counted along ITS sweep) sits at x = xo - DIRX * k
     const int xo = (DIRX > 0 ? d.W1 - 1 : 0) - DIRX * (j * K);
@@ -604,12 +941,12 @@ __device__ __forceinline__ void horiz_segment(const SgbmDims& d, const HorizRow<
         } else {
 #pragma unroll
             for (int r = 0; r < NPR; r++) o.L[r] = ckv[r];
-            o.m = vec_min<NPR>(o.L);
+            o.mm = vec_min<32, NPR>(o.L, pl);
         }
 #pragma unroll
         for (int i = 0; i < K; i++) {
             if (FULL || i < cnt) {
-                path_step<NPR, PAD>(o, cb[i], padmask, P1P1, P2, lane_first, lane_last);
+                path_step<32, NPR, PAD>(o, cb[i], padmask, P1P1, P2P2, pl);
 #pragma unroll
                 for (int r = 0; r < NPR; r++) sv[i][r] = o.L[r];
             }
@@ -618,15 +955,15 @@ __device__ __forceinline__ void horiz_segment(const SgbmDims& d, const HorizRow<
         for (int i = K - 1; i >= 0; i--) {
             if (FULL || i < cnt) {
 #pragma unroll
-                for (int r = 0; r < NPR; r++)
-                    sv[i][r] = __viaddmin_u16x2(__viaddmin_u16x2(__viaddmin_u16x2(lv[0][i][r], lv[1][i][r], kMaxC2), lv[2][i][r], kMaxC2),
-                                                sv[i][r], kMaxC2);
+                for (int v = 0; v < horiz_nreg<NV>(); v++)
+#pragma unroll
+                    for (int r = 0; r < NPR; r++) sv[i][r] = __viaddmin_u16x2(sv[i][r], lv[v][i][r], kMaxC2);
             }
         }
     }
-    if (HH) {  // MODE_HH: the three bottom-up paths Lv[3..5]
+    if (NV > 3) {  // MODE_HH: the three bottom-up paths Lv[3..5]
 #pragma unroll
-        for (int v = 3; v < 6; v++) {
+        for (int v = 3; v < NV; v++) {
 #pragma unroll
             for (int i = K - 1; i >= 0; i--) {
                 if (FULL || i < cnt) {
@@ -647,13 +984,13 @@ __device__ __forceinline__ void horiz_segment(const SgbmDims& d, const HorizRow<
 #pragma unroll
         for (int i = 0; i < K; i++) ldv<NPR>(cn[i], pn - i * DS);
         if (j > 1) ldv<NPR>(ckn, R.ck_oth + (size_t)(j - 1) * WPC);
-        horiz_load_lv<NPR, DIRX, true>(R, o0 + K * DS, K, lv);
+        horiz_load_lv<NPR, NV, DIRX, true>(R, o0 + K * DS, K, lv);
     }
     // own path over the segment, in the own direction (= the other's, reversed)
 #pragma unroll
     for (int i = K - 1; i >= 0; i--) {
         if (FULL || i < cnt) {
-            path_step<NPR, PAD>(s, cb[i], padmask, P1P1, P2, lane_first, lane_last);
+            path_step<32, NPR, PAD>(s, cb[i], padmask, P1P1, P2P2, pl);
             uint32_t S[NPR];
 #pragma unroll
             for (int r = 0; r < NPR; r++) S[r] = __viaddmin_u16x2(sv[i][r], s.L[r], kMaxC2);
@@ -676,17 +1013,19 @@ __device__ __forceinline__ void horiz_segment(const SgbmDims& d, const HorizRow<
     }
 }
 
-template <int NPR, bool PAD, bool HH, bool BATCH, int DIRX>
+template <int NPR, bool PAD, int NV, bool BATCH, int DIRX>
 __device__ __forceinline__ void horiz_phase2(const SgbmDims& d, const HorizRow<NPR>& R, PathState<NPR>& s, int lane) {
     constexpr int WPC = 32 * NPR, K = horiz_seg<NPR>(), DS = DIRX * WPC;
     const int n2 = R.n2;
     if (n2 <= 0) return;
     uint32_t padmask[NPR];
-    make_padmask<NPR>(padmask, lane, d.D);
-    const uint32_t P1P1 = bcast16(d.P1), P2 = d.P2;
+    make_padmask<32, NPR>(padmask, lane, d.D);
+    const uint32_t P1P1 = bcast16(d.P1), P2P2 = bcast16(d.P2);
+    PathLane<32> pl;
+    pl.init(lane);
     int j = (n2 + K - 1) / K - 1;
     int cnt = n2 - j * K;
-    uint32_t cb[K][NPR], ckv[NPR], lv[3][K][NPR];
+    uint32_t cb[K][NPR], ckv[NPR], lv[horiz_nreg<NV>()][K][NPR];
 #pragma unroll
     for (int r = 0; r < NPR; r++) ckv[r] = 0;
     {
@@ -695,16 +1034,16 @@ __device__ __forceinline__ void horiz_phase2(const SgbmDims& d, const HorizRow<N
         for (int i = 0; i < K; i++)
             if (i < cnt) ldv<NPR>(cb[i], R.C + o0 - i * DS);
         if (j > 0) ldv<NPR>(ckv, R.ck_oth + (size_t)j * WPC);
-        horiz_load_lv<NPR, DIRX, false>(R, o0, cnt, lv);
+        horiz_load_lv<NPR, NV, DIRX, false>(R, o0, cnt, lv);
     }
     if (cnt < K) {
-        horiz_segment<NPR, PAD, HH, BATCH, DIRX, false>(d, R, s, lane, j, cnt, cb, ckv, lv, padmask, P1P1, P2);
+        horiz_segment<NPR, PAD, NV, BATCH, DIRX, false>(d, R, s, lane, j, cnt, cb, ckv, lv, padmask, P1P1, P2P2, pl);
         j--;
     }
-    for (; j >= 0; j--) horiz_segment<NPR, PAD, HH, BATCH, DIRX, true>(d, R, s, lane, j, K, cb, ckv, lv, padmask, P1P1, P2);
+    for (; j >= 0; j--) horiz_segment<NPR, PAD, NV, BATCH, DIRX, true>(d, R, s, lane, j, K, cb, ckv, lv, padmask, P1P1, P2P2, pl);
 }
 
-template <int NPR, bool PAD, bool HH, bool BATCH>
+template <int NPR, bool PAD, int NV, bool BATCH>
 __global__ void __launch_bounds__(64, NPR == 4 ? 6 : OVO_HOR_MINB) k_sgbm_horiz(SgbmDims d, SgbmWorkspace ws, size_t ws_stride) {
     OVO_DYN_SMEM(uint32_t, hsm);
     uint32_t* d2key = hsm;                                        // [W]
@@ -744,8 +1083,8 @@ __global__ void __launch_bounds__(64, NPR == 4 ? 6 : OVO_HOR_MINB) k_sgbm_horiz(
     if (wid == 0) horiz_phase1<NPR, PAD, 1>(d, R, s, lane);
     else horiz_phase1<NPR, PAD, -1>(d, R, s, lane);
     __syncthreads();
-    if (wid == 0) horiz_phase2<NPR, PAD, HH, BATCH, 1>(d, R, s, lane);
-    else horiz_phase2<NPR, PAD, HH, BATCH, -1>(d, R, s, lane);
+    if (wid == 0) horiz_phase2<NPR, PAD, NV, BATCH, 1>(d, R, s, lane);
+    else horiz_phase2<NPR, PAD, NV, BATCH, -1>(d, R, s, lane);
     __syncthreads();
     // ---- uniqueness, sub-pixel refinement and disp2 (A.4.4), data-parallel over the row
     {
@@ -926,11 +1265,48 @@ __global__ void __launch_bounds__(256) k_ccl_apply(const int16_t* __restrict__ i
     }
 }
 
+// the fused vertical kernel is the default for MODE_SGBM; OVO_SGBM_FUSED=0 selects the one-volume-per-direction kernel
+// (k_sgbm_vert, also what MODE_HH uses) for A/B measurements
+static bool use_fused_vertical() {
+    static const bool on = [] {
+        const char* e = getenv("OVO_SGBM_FUSED");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
+template <int LPC, int NPR, bool PAD, int BR, int VG>
+int launch_vsum(const SgbmDims& d, const SgbmWorkspace& ws, size_t ws_stride, int nb, cudaStream_t st) {
+    constexpr int B = vs_tile<LPC, VG>();
+    const size_t smem = ((size_t)kVsRing * B + (size_t)kVsStrips * (B + 2 * BR)) * LPC * NPR * 4 + kVsStrips * 8;
+    auto k_sgbm_vsum_t = k_sgbm_vsum<LPC, NPR, PAD, BR, VG>;
+    if (smem > 48 * 1024) OVO_CUDA(cudaFuncSetAttribute(k_sgbm_vsum_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const dim3 grid(cdiv(d.W1, B), nb), block(32 * vs_warps<LPC, BR, VG>());
+    for (int y0 = 0, band = 0; y0 < d.H; y0 += BR, band++) {
+        OVO_LAUNCH(k_sgbm_vsum_t, grid, block, smem, st, d, ws, ws_stride, y0, band & 1);
+        OVO_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
 template <int NPR, bool PAD>
 int launch_paths(const SgbmDims& d, const SgbmWorkspace& ws, size_t ws_stride, int nb, cudaStream_t st) {
-    dim3 gv((d.mode ? 6 : 3) * cdiv(d.W1, 8), nb);
-    { auto k_sgbm_vert_t = k_sgbm_vert<NPR, PAD>; OVO_LAUNCH(k_sgbm_vert_t, gv, dim3(256), 0, st, d, ws, ws_stride); }
-    OVO_LAUNCH_CHECK();
+    // the band-state buffer of the fused kernel lives in the second volume: 6 * W1 vectors must fit into two volumes
+    const bool fused = d.mode == 0 && d.H >= 4 && use_fused_vertical();
+    if (fused) {
+        int rc;
+#ifndef OVO_VS_VG
+#define OVO_VS_VG 8
+#endif
+        if constexpr (NPR == 1) rc = launch_vsum<8, 4, PAD, 16, OVO_VS_VG>(d, ws, ws_stride, nb, st);        // Dp = 64
+        else if constexpr (NPR == 2) rc = launch_vsum<8, 8, PAD, 16, OVO_VS_VG>(d, ws, ws_stride, nb, st);   // Dp = 128
+        else rc = launch_vsum<16, 8, PAD, 8, 16>(d, ws, ws_stride, nb, st);                                  // Dp = 256
+        if (rc) return rc;
+    } else {
+        dim3 gv((d.mode ? 6 : 3) * cdiv(d.W1, 8), nb);
+        { auto k_sgbm_vert_t = k_sgbm_vert<NPR, PAD>; OVO_LAUNCH(k_sgbm_vert_t, gv, dim3(256), 0, st, d, ws, ws_stride); }
+        OVO_LAUNCH_CHECK();
+    }
     dim3 gh(d.H, nb);
     const size_t smem = (size_t)d.W * 6 + (size_t)d.W1 * 10 + 16;
     auto go = [&](auto k_sgbm_horiz_t) -> int {
@@ -939,8 +1315,8 @@ int launch_paths(const SgbmDims& d, const SgbmWorkspace& ws, size_t ws_stride, i
         return 0;
     };
     int rc;
-    if (d.uniq < 100) rc = d.mode ? go(k_sgbm_horiz<NPR, PAD, true, true>) : go(k_sgbm_horiz<NPR, PAD, false, true>);
-    else rc = d.mode ? go(k_sgbm_horiz<NPR, PAD, true, false>) : go(k_sgbm_horiz<NPR, PAD, false, false>);
+    if (d.uniq < 100) rc = fused ? go(k_sgbm_horiz<NPR, PAD, 1, true>) : (d.mode ? go(k_sgbm_horiz<NPR, PAD, 6, true>) : go(k_sgbm_horiz<NPR, PAD, 3, true>));
+    else rc = fused ? go(k_sgbm_horiz<NPR, PAD, 1, false>) : (d.mode ? go(k_sgbm_horiz<NPR, PAD, 6, false>) : go(k_sgbm_horiz<NPR, PAD, 3, false>));
     if (rc) return rc;
     OVO_LAUNCH_CHECK();
     return 0;

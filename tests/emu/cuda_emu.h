@@ -220,10 +220,11 @@ static inline unsigned __match_any_sync(unsigned, int v) {
 }
 static inline int __any_sync(unsigned m, int p) { return __ballot_sync(m, p) != 0; }
 static inline int __all_sync(unsigned m, int p) { const int n = ovo_emu::warp_lanes(); return __ballot_sync(m, p) == (n == 32 ? 0xffffffffu : ((1u << n) - 1)); }
-static inline unsigned __reduce_min_sync(unsigned, unsigned v) {
+static inline unsigned __reduce_min_sync(unsigned mask, unsigned v) {  // sub-warp masks: every lane names its own group
     const uint64_t* b = ovo_emu::warp_gather(v);
     unsigned r = 0xffffffffu;
-    for (int i = 0; i < ovo_emu::warp_lanes(); i++) r = std::min(r, (unsigned)b[i]);
+    for (int i = 0; i < ovo_emu::warp_lanes(); i++)
+        if (mask & (1u << i)) r = std::min(r, (unsigned)b[i]);
     return r;
 }
 static inline unsigned __reduce_max_sync(unsigned, unsigned v) {

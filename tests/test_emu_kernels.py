@@ -54,8 +54,26 @@ class Ctx:
     (330, 16, 256, 1, dict(_d=62)),
     (282, 16, 208, 1, dict(blockSize=3, P1=72, P2=288)),                        # padded 208 -> 256
     (160, 20, 64, 1, dict(uniquenessRatio=100)),                                # uniquenessRatio >= 100: cell-by-cell selection
+    (265, 33, 128, 1, dict(_d=20)),                                             # fused vertical kernel: 3 tiles x 3 bands, last band = 1 row
+    (140, 18, 128, 1, dict(_d=3)),                                              # W1 = 12: narrower than the halo of a tile
+    (353, 17, 256, 1, dict(_d=40)),                                             # 256 disparities: 4 tiles of 32 columns, bands of 8 rows
 ])
 def test_sgbm_kernels(emu, W, H, D, nb, kw):
+    _sgbm_case(emu, W, H, D, nb, kw)
+
+
+def test_sgbm_kernels_one_volume_per_direction(emu, monkeypatch):
+    """The unfused vertical kernel (OVO_SGBM_FUSED=0; what MODE_HH builds on) stays bit-exact too.  The switch is read once per
+    process, so this runs in a child interpreter."""
+    import subprocess
+    code = ("import sys; sys.path[:0] = [%r, %r, %r]; import test_emu_kernels as T, build_emu; from openvo_b200 import _native as N; "
+            "lib = N.load(build_emu.build()); T._sgbm_case(lib, 200, 34, 128, 2, {}); T._sgbm_case(lib, 300, 17, 256, 1, dict(_d=31)); "
+            "T._sgbm_case(lib, 170, 19, 96, 1, dict(blockSize=3, P1=72, P2=288, disp12MaxDiff=2))"
+            % (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "emu")))
+    subprocess.run([sys.executable, "-c", code], check=True, env=dict(os.environ, OVO_SGBM_FUSED="0"))
+
+
+def _sgbm_case(emu, W, H, D, nb, kw):
     kw = dict(kw)
     shift = kw.pop("_d", 7)
     p = sgbm_params(D, **kw)
