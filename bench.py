@@ -102,6 +102,120 @@ def run_cpu(cfg_key, L, R, warmup, steps, nprocs):
     return nprocs * steps / wall, wall
 
 
+def cpu_profile_worker(cfg_key, frames_file, nframes):
+    """Single-stream figure (what a user of the reference gets: one process, cv2's default thread pool) and per-stage medians
+    of the reference's CPU path: each cv2 call of update() timed in place.  Prints one JSON line."""
+    import cv2
+    from openvo_b200 import synth
+    from oracle import openvo_port as O
+    cfg = CONFIGS[cfg_key]
+    z = np.load(frames_file)
+    L, R = z["L"], z["R"]
+    args = synth.camera_args(cfg["W"], cfg["H"], cfg["D"])
+    od = O.StereoOdometerPort(O.StereoCameraPort(**args, backend="cv2"), nfeatures=cfg["n"], preprocessed_frames=True)
+    stages = {}
+
+    def timed(obj, name, tag):
+        fn = getattr(obj, name)
+
+        def wrap(*a, **k):
+            t0 = time.perf_counter()
+            out = fn(*a, **k)
+            stages.setdefault(tag, []).append(time.perf_counter() - t0)
+            return out
+        setattr(obj, name, wrap)
+    timed(od.stereo.be, "disparity", "sgbm")          # ref: stereo_camera.py:51
+    timed(od.stereo.be, "reproject", "reproject")     # ref: stereo_camera.py:52
+    timed(od.be, "features", "orb")                   # ref: stereo_odometer.py:117
+    timed(od.be, "knn2", "knn")                       # ref: stereo_odometer.py:163
+    timed(od.be, "rigid", "umeyama")                  # ref: stereo_odometer.py:190,204
+    pc = od.point_clouds
+
+    def point_clouds(*a, **k):                        # ref: stereo_odometer.py:162-175 (knn + ratio test + the bilinear loop)
+        t0 = time.perf_counter()
+        out = pc(*a, **k)
+        stages.setdefault("point_clouds_total", []).append(time.perf_counter() - t0)
+        return out
+    od.point_clouds = point_clouds
+    for s in range(2):
+        od.update(L[frame_index(s, 0)], R[frame_index(s, 0)])
+    for v in stages.values():
+        v.clear()
+    t0 = time.perf_counter()
+    for s in range(2, 2 + nframes):
+        od.update(L[frame_index(s, 0)], R[frame_index(s, 0)])
+    wall = time.perf_counter() - t0
+    med = {k: 1e3 * float(np.median(v)) for k, v in stages.items() if v}
+    if "point_clouds_total" in med and "knn" in med:
+        med["bilinear_loop"] = med.pop("point_clouds_total") - med["knn"]   # ref: stereo_odometer.py:172-174
+    print(json.dumps({"single_stream_fps": nframes / wall, "cv2_threads": cv2.getNumThreads(), "frames": nframes, "stages_ms": med}))
+
+
+def run_cpu_profile(cfg_key, L, R, nframes):
+    with tempfile.NamedTemporaryFile(suffix=".npz", delete=False) as fh:
+        np.savez(fh, L=L, R=R)
+        frames_file = fh.name
+    try:
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--_cpu_profile", cfg_key, frames_file, str(nframes)],
+                             capture_output=True, text=True, timeout=600)
+        return json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as e:  # pragma: no cover
+        return {"error": repr(e)}
+    finally:
+        os.unlink(frames_file)
+
+
+def frame_sharded_4k(rank, world, n_frames=16, n_render=4):
+    """BASELINE config 4: ONE 3840x2160 / ORB 10000 / 256-disparity sequence sharded by contiguous frame chunk over the ranks
+    (openvo_b200.dist.run_frame_chunk: one-frame halo, no data-path collective), per-frame transforms all-gathered once over
+    NCCL, chain replayed; rank 0 also runs the sequence sequentially and the two chains are compared."""
+    import torch
+    import torch.distributed as dist
+    from openvo_b200 import StereoCamera, StereoOdometer, synth
+    from openvo_b200 import dist as odist
+    cfg = CONFIGS["U"]
+    Lr, Rr, _ = synth.make_sequence(cfg["W"], cfg["H"], n_render)   # every rank renders the same deterministic frames
+    period = 2 * (n_render - 1)
+    idx = [(k % period) if (k % period) < n_render else period - (k % period) for k in range(n_frames)]
+    lefts, rights = [Lr[i] for i in idx], [Rr[i] for i in idx]
+    cam = StereoCamera(**synth.camera_args(cfg["W"], cfg["H"], cfg["D"]))
+    od = StereoOdometer(cam, nfeatures=cfg["n"], preprocessed_frames=True)
+    od.update(lefts[0], rights[0])          # warm-up (allocations, first launches), then a fresh state machine
+    od = StereoOdometer(cam, nfeatures=cfg["n"], preprocessed_frames=True)
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    start, T, st = odist.run_frame_chunk(od, lefts, rights, rank, world)
+    Tall, sall = odist.gather_frame_chunks(start, T, st, n_frames)
+    chain = odist.replay_chains(Tall[None], sall[None])[0]
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    rec = None
+    if rank == 0:
+        seq = StereoOdometer(cam, nfeatures=cfg["n"], preprocessed_frames=True)
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        oks = [seq.update(lefts[k], rights[k]) for k in range(n_frames)]
+        s1.record()
+        torch.cuda.synchronize()
+        dR = chain[:3, :3] @ seq.c_T_w[:3, :3].T
+        ang = float(np.arccos(np.clip((np.trace(dR) - 1) / 2, -1, 1)))
+        dt = float(np.linalg.norm(chain[:3, 3] - seq.c_T_w[:3, 3]))
+        rec = {"workload": "one synthetic %s sequence of %d frames, sharded by contiguous frame chunk (one-frame halo)" % (cfg["name"], n_frames),
+               "value": n_frames / (ms * 1e-3), "unit": "frames/s", "ms": ms, "n_gpus": world,
+               "sequential_1gpu_frames_per_s": n_frames / (s0.elapsed_time(s1) * 1e-3),
+               "frames_committed": int(sum(1 for v in sall[1:] if v)) + 1, "frames": n_frames, "sequential_committed": int(sum(oks)),
+               "chain_equals_sequential": bool(np.array_equal(chain, seq.c_T_w)),
+               "chain_vs_sequential": {"rotation_rad": ang, "translation": dt}}
+    dist.barrier()
+    return rec
+
+
 def host_cores():
     try:
         n = len(os.sched_getaffinity(0))
@@ -148,20 +262,29 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def algorithmic_bytes(tag, eng, nb):
+def algorithmic_bytes(tag, eng, nb, fused=True):
     """ALGORITHMIC HBM bytes of one launch of the named kernel (DESIGN.md 'Kernels'); V = one frame's cost volume."""
     D = eng.cfg.sgbm.numDisparities
     Dp = 64 if D <= 64 else (128 if D <= 128 else 256)
     W, H = eng.W, eng.H
     V = H * (W - D) * Dp * 2
+    bands = -(-H // (8 if Dp == 256 else 16))  # launches of the fused vertical kernel per batch (one per band of rows)
     table = {
         "k_sgbm_prep": 2 * W * H + 16 * W * H,
         "k_sgbm_cost_t": 16 * W * H + V,
-        "k_sgbm_vert_t": V + 3 * V,
-        "k_sgbm_horiz_t": V + 3 * V + 2 * W * H,
-        "k_sgbm_paths_t": V + 2 * W * H,
+        "k_sgbm_vert_t": V + 3 * V,                                          # unfused (OVO_SGBM_FUSED=0 / MODE_HH): C in, three volumes out
+        "k_sgbm_vsum_t": 2.0 * V / bands,                                    # fused: C in, Sv out, one band per launch
+        "k_sgbm_horiz_t": (2 * V if fused else 4 * V) + 2 * W * H,           # C + the vertical sums in, disparity out
     }
     return table.get(tag, 0) * nb
+
+
+def source_sha1():
+    """sha1 of the SGBM kernel source: stamps profiles/traffic.json, so a captured DRAM figure is only quoted for the code it
+    was captured from (the GPU box has no .git)."""
+    import hashlib
+    with open(os.path.join(ROOT, "openvo_b200", "csrc", "sgbm.cu"), "rb") as fh:
+        return hashlib.sha1(fh.read()).hexdigest()[:16]
 
 
 def main():
@@ -181,17 +304,26 @@ def main():
                          "thread finishes batch g of step s, queues batch g of step s+1 and moves on to g+1, so the host-side "
                          "keypoint selection of one batch overlaps device work of the others")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the extra records of the default run (other_configs: short F and U runs; frame-sharded 4K at N > 1)")
     ap.add_argument("--_cpu_worker", nargs=5, default=None)
+    ap.add_argument("--_cpu_profile", nargs=3, default=None)
     a = ap.parse_args()
     if a._cpu_worker:
         k, f, seq, wu, st = a._cpu_worker
         return cpu_worker(k, f, int(seq), int(wu), int(st))
+    if a._cpu_profile:
+        k, f, n = a._cpu_profile
+        return cpu_profile_worker(k, f, int(n))
     cfg = CONFIGS[a.config]
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     workload = "synthetic %s, independent sequences advanced 1 frame each per step" % cfg["name"]
     metric, unit = "stereo frames/sec", "frames/s"
+    # `config` is identical in both arms (the driver compares it); per-arm run details go to `run`
+    config = {"workload": workload, "width": cfg["W"], "height": cfg["H"], "nfeatures": cfg["n"], "num_disparities": cfg["D"],
+              "distinct_frames": N_DISTINCT}
 
     L, R = make_frames(cfg)
 
@@ -201,10 +333,11 @@ def main():
         cores = host_cores()
         fps, wall = run_cpu(a.config, L, R, max(a.warmup, 1), a.steps, cores)
         sample = "%d processes x %d frames each (cv2.setNumThreads(1)), wall %.1f s" % (cores, a.steps, wall)
+        config["l2_policy"] = "no flush: the working set of a step (>= 0.47 GB of SGBM volumes per frame) is far larger than the 126 MB L2"
         line = {"impl": "reference", "metric": metric, "value": fps, "unit": unit, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": 1e3 * wall / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i16",
-                "data": "synthetic", "config": {"workload": workload, "frames_per_step": cores, "sequences": cores,
-                                                "note": "one sequence per host core"},
+                "data": "synthetic", "config": config,
+                "run": {"frames_per_step": cores, "sequences": cores, "note": "one single-threaded reference process per host core"},
                 "cpu_baseline": {"value": fps, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
                 "e2e": {"value": fps, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         print(json.dumps(line))
@@ -219,6 +352,11 @@ def main():
         cpu_baseline = {"value": fps, "unit": unit, "cores": cores, "kind": "port",
                         "sample": "oracle port on cv2 (the reference's CPU path): %d processes x %d frames (cv2 threads=1 each), "
                                   "wall %.1f s" % (cores, nfr, wall)}
+        # what a user of the reference gets from one update() stream, and where its time goes
+        prof = run_cpu_profile(a.config, L, R, 12 if a.config == "K" else 3)
+        cpu_baseline["single_stream"] = {"value": prof.get("single_stream_fps"), "unit": unit, "cv2_threads": prof.get("cv2_threads"),
+                                         "frames": prof.get("frames")}
+        cpu_baseline["stages_ms_per_frame"] = prof.get("stages_ms")
 
     if "OVO_SELECT_THREADS" not in os.environ:
         os.environ["OVO_SELECT_THREADS"] = str(a.select_threads or max(2, min(8, host_cores() // max(1, world))))
@@ -261,8 +399,9 @@ def main():
             ti = torch.tensor(idx, device="cuda")
             bo.begin_device(dev_L[ti], dev_R[ti])
 
-    def run_part(bos_t, t, steps, first_step, host):
-        """One host thread, NG batches round-robin: finish batch g of step s, queue batch g of step s+1, go on to batch g+1."""
+    def run_part(bos_t, t, steps, first_step, host, hist=None):
+        """One host thread, NG batches round-robin: finish batch g of step s, queue batch g of step s+1, go on to batch g+1.
+        hist (optional): [T [S, steps, 4, 4], status [S, steps]] filled with every frame's relative transform / commit mode."""
         ok = 0
         for g in range(NG):
             with torch.cuda.stream(streams[t][g]):
@@ -270,19 +409,26 @@ def main():
         for s in range(first_step, first_step + steps):
             for g in range(NG):
                 with torch.cuda.stream(streams[t][g]):
-                    ok += sum(bos_t[g].finish())
+                    res = bos_t[g].finish()
+                    ok += sum(res)
+                    if hist is not None:
+                        base = (t * NG + g) * SP
+                        for q, od in enumerate(bos_t[g].odometers):
+                            if res[q] and od.last_mode:
+                                hist[0][base + q, s - first_step] = od.last_T
+                                hist[1][base + q, s - first_step] = od.last_mode
                     if s + 1 < first_step + steps:
                         begin(bos_t[g], t, g, s + 1, host)
         return ok
 
-    def run(bos, steps, first_step, host):
+    def run(bos, steps, first_step, host, hist=None):
         oks, errs = [0] * NT, []
         torch.cuda.synchronize()
 
         def work(t):
             try:
                 torch.cuda.set_device(local_rank)
-                oks[t] = run_part(bos[t], t, steps, first_step, host)
+                oks[t] = run_part(bos[t], t, steps, first_step, host, hist)
             except Exception as e:  # pragma: no cover
                 errs.append(e)
         if NT == 1:
@@ -310,12 +456,12 @@ def main():
         sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        ok = run(bos, a.steps, warmup, host)
-        if world > 1:  # the only exchange: per-frame relative transforms + status, once per chunk
-            ods = [od for bt in bos for b in bt for od in b.odometers]
-            T = np.stack([od.last_T if od.last_T is not None else np.eye(4) for od in ods])[:, None]
-            st = np.ones((S, 1), np.int32)
-            odist.gather_poses(T, st, odist.shard_sequences(S * world, rank, world), S * world)
+        hist = [np.tile(np.eye(4), (S, a.steps, 1, 1)), np.zeros((S, a.steps), np.int32)]
+        ok = run(bos, a.steps, warmup, host, hist)
+        chains = None
+        if world > 1:  # the only exchange: every frame's relative transform + commit mode of the chunk, gathered once
+            Tall, sall, _ = odist.gather_poses(hist[0], hist[1], odist.shard_sequences(S * world, rank, world), S * world)
+            chains = odist.replay_chains(Tall, sall)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -330,7 +476,7 @@ def main():
                 for od in b.odometers:
                     key = od.skip_cause or "none"
                     causes[key] = causes.get(key, 0) + 1
-        return dict(ms=ms, ok=ok, causes=causes, h2d=(sum(e.h2d_bytes for e in engs) - h2d0) / a.steps, d2h=(sum(e.d2h_bytes for e in engs) - d2h0) / a.steps,
+        return dict(ms=ms, ok=ok, causes=causes, chains=chains, h2d=(sum(e.h2d_bytes for e in engs) - h2d0) / a.steps, d2h=(sum(e.d2h_bytes for e in engs) - d2h0) / a.steps,
                     launches=lib.ovo_launch_count() - l0, clocks=clocks, bos=bos)
 
     dev = timed(host=False)
@@ -338,6 +484,21 @@ def main():
     frames = S * world * a.steps
     value = frames / (dev["ms"] * 1e-3)
     e2e_value = frames / (e2e["ms"] * 1e-3)
+
+    # ---- verification: sequence 0 of this rank replayed frame by frame through the single-stream StereoOdometer.update()
+    # must land on exactly the pose the batched, two-streams-in-flight run produced (same kernels, different driver)
+    from openvo_b200 import StereoOdometer
+    import hashlib
+    single = StereoOdometer(cam, nfeatures=cfg["n"], preprocessed_frames=True, _engine_tag=999)
+    for s_ in range(warmup + a.steps):
+        i = frame_index(s_, rank * S)
+        single.update(L[i], R[i])
+    od0 = dev["bos"][0][0].odometers[0]
+    e2e0 = e2e["bos"][0][0].odometers[0]
+    verified = bool(np.array_equal(single.c_T_w, od0.c_T_w) and np.array_equal(single.c_T_w, e2e0.c_T_w) and
+                    single.skip_cause == od0.skip_cause and single.skipped_frames == od0.skipped_frames)
+    pose_hash = hashlib.sha1(np.ascontiguousarray(np.stack([od.c_T_w for bt in dev["bos"] for b in bt for od in b.odometers])).tobytes()).hexdigest()[:16]
+    del single
 
     # ---- roofline leg: per-kernel CUDA-event durations over an identical region (events on the launching stream)
     roofline, per_kernel = None, {}
@@ -361,12 +522,14 @@ def main():
         except Exception:
             pass
         peak, which = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
-        abytes = algorithmic_bytes(top, b0.engine, SP)
+        abytes = algorithmic_bytes(top, b0.engine, SP, fused="k_sgbm_vsum_t" in prof)
         dur_s = prof[top][0] / prof[top][1] * 1e-3
         achieved = abytes / dur_s / 1e9 if dur_s > 0 else 0.0
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(a.config, {}).get(top)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            if tj.get("source_sha1") == source_sha1():   # a capture of other code says nothing about this build: report null
+                traffic = tj.get(a.config, {}).get(top)
         except Exception:
             pass
         roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": which, "unit": "GB/s",
@@ -397,7 +560,11 @@ def main():
         stages = {
             "stage4_sgbm": {"ms_per_frame": t4, "int_ops_per_frame": ops4, "achieved_gops": ops4 / (t4 * 1e-3) / 1e9 if t4 else None,
                             "peak_gops": int_peak, "frac": (ops4 / (t4 * 1e-3) / 1e9 / int_peak) if (t4 and int_peak) else None,
-                            "peak_source": "profiles/int_peaks.json int32_add_logic (measured, tools/int_peak.cu)"},
+                            "peak_source": "profiles/int_peaks.json int32_add_logic (measured, tools/int_peak.cu)",
+                            "frac_of_dpx_int16_peak": (ops4 / (t4 * 1e-3) / 1e9 / ipk["dpx_viaddmnmx_u16x2_int16_gops"])
+                            if (t4 and ipk.get("dpx_viaddmnmx_u16x2_int16_gops")) else None,
+                            "note": "the path kernels run packed int16 on the half-rate DPX pipe (VIADDMNMX.U16x2): the DPX figure counts two "
+                                    "int16 operations per lane instruction"},
             "stage12_orb": {"ms_per_frame": t12, "bytes_per_frame": bytes12, "achieved_gbs": bytes12 / (t12 * 1e-3) / 1e9 if t12 else None,
                             "peak_gbs": peak, "frac": (bytes12 / (t12 * 1e-3) / 1e9 / peak) if t12 else None, "keypoints": nkp,
                             "note": "device kernels only; the retainBest host step is outside"},
@@ -406,20 +573,48 @@ def main():
                              "peak_source": "profiles/int_peaks.json popc_xor_add (measured)"},
             "stage5_pose": {"ms_per_frame": t5, "note": "latency-bound; no roofline (SURVEY.md §8(d))"},
         }
+    # ---- extra records (default run only) -------------------------------------------------------------------------------
+    run_info = {"frames_per_step": S * world, "sequences_per_gpu": S, "host_threads": NT, "batches_in_flight_per_thread": NG,
+                "sequences_per_batch": SP, "workspace_gb_per_frame": dev["bos"][0][0].engine.workspace.numel() / max(1, SP) / 1e9,
+                "frames_committed": dev["ok"], "frames": S * a.steps, "last_skip_cause_per_sequence": dev["causes"],
+                "pose_hash": pose_hash}
+    if dev["chains"] is not None:  # chains of the timed chunk, replayed on every rank from the all-gathered per-frame transforms
+        run_info["gathered_chains"] = int(dev["chains"].shape[0])
+        run_info["gathered_chains_hash"] = hashlib.sha1(np.ascontiguousarray(dev["chains"]).tobytes()).hexdigest()[:16]
+    extras = {}
+    if not a.no_extras:
+        # free this configuration's workspaces first: 4K needs 16 GB per frame in flight
+        del dev["bos"], e2e["bos"], od0, e2e0
+        bos = b0 = eng0 = None
+        cam._engines.clear()
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        if world > 1:
+            extras["frame_sharded_4k"] = frame_sharded_4k(rank, world)
+        elif a.config == "K":
+            other = {}
+            for key, steps in (("F", 5), ("U", 4)):
+                try:
+                    out = subprocess.run([sys.executable, os.path.abspath(__file__), "--config", key, "--steps", str(steps), "--warmup", "3",
+                                          "--no-cpu-baseline", "--no-extras"], capture_output=True, text=True, timeout=900)
+                    d_ = json.loads(out.stdout.strip().splitlines()[-1])
+                    other[key] = {k: d_[k] for k in ("value", "unit", "ms_per_step", "steps", "config", "run", "verified", "clocks", "gpu_launches")}
+                    other[key]["e2e"] = d_["e2e"]
+                    other[key]["stages"] = {k: {"ms_per_frame": v.get("ms_per_frame"), "frac": v.get("frac")} for k, v in (d_.get("stages") or {}).items()}
+                except Exception as e:  # pragma: no cover
+                    other[key] = {"error": repr(e)}
+            extras["other_configs"] = other
     if rank == 0:
+        config["l2_policy"] = "no flush: the working set of a step (>= 0.47 GB of SGBM volumes per frame) is far larger than the 126 MB L2"
         line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": a.steps, "warmup": warmup,
                 "ms_per_step": dev["ms"] / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i16",
-                "data": "synthetic",
-                "config": {"workload": workload, "frames_per_step": S * world, "sequences_per_gpu": S, "host_threads": NT, "batches_in_flight_per_thread": NG,
-                           "sequences_per_batch": SP, "distinct_frames": N_DISTINCT,
-                           "l2_policy": "inputs+working set larger than L2: %d frames x %.2f GB of SGBM volumes per step" % (
-                               S, dev["bos"][0][0].engine.workspace.numel() / max(1, SP) / 1e9),
-                           "frames_committed": dev["ok"], "frames": S * a.steps,
-                           "last_skip_cause_per_sequence": dev["causes"]},
+                "data": "synthetic", "config": config, "run": run_info, "verified": verified,
                 "clocks": dev["clocks"], "gpu_launches": dev["launches"],
                 "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                         "ms_per_step": e2e["ms"] / a.steps},
                 "roofline": roofline, "stages": stages, "kernels": per_kernel}
+        line.update(extras)
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line))

@@ -293,6 +293,14 @@ __device__ __forceinline__ void make_padmask(uint32_t (&padmask)[NPR], int lane,
     }
 }
 
+// a + b per 16-bit half, saturating at MAX_COST unless the parameters guarantee that no sum of path costs can reach it
+// (launch_paths: 5 * (blockSize^2 * (2 * ftzero + 63) + P2) <= 32000); the plain add is a full-rate instruction, the
+// saturating one a half-rate DPX instruction
+template <bool SAT>
+__device__ __forceinline__ uint32_t sum16(uint32_t a, uint32_t b) {
+    return SAT ? __viaddmin_u16x2(a, b, kMaxC2) : a + b;
+}
+
 template <int NPR>
 __device__ __forceinline__ void ldv(uint32_t (&v)[NPR], const uint32_t* p) {
     if constexpr (NPR % 4 == 0) {
@@ -522,7 +530,7 @@ template <int LPC>
 __device__ __forceinline__ int vs_chunk(int q, int i) { return (i * LPC + q) * 4; }
 
 // The three directions of a cell meet in the ring: V stores, D1 adds, D3 adds and writes the sum to Sv.
-template <int LPC, int NPR, int BR>
+template <int LPC, int NPR, int BR, bool SAT>
 __device__ __forceinline__ void vs_meet(const VsSlot<NPR>& sl, int q, uint32_t* ring, uint32_t* __restrict__ Sv) {
     constexpr int DH = LPC * NPR;
     uint32_t* cell = ring + sl.rbase + (sl.scol - (BR * DH + q * NPR));
@@ -538,7 +546,7 @@ __device__ __forceinline__ void vs_meet(const VsSlot<NPR>& sl, int q, uint32_t* 
             a[4 * i] = v.x; a[4 * i + 1] = v.y; a[4 * i + 2] = v.z; a[4 * i + 3] = v.w;
         }
 #pragma unroll
-        for (int k = 0; k < NPR; k++) a[k] = __viaddmin_u16x2(a[k], sl.s.L[k], kMaxC2);
+        for (int k = 0; k < NPR; k++) a[k] = sum16<SAT>(a[k], sl.s.L[k]);
         if (sl.kind == 1) {
 #pragma unroll
             for (int i = 0; i < NPR / 4; i++)
@@ -558,7 +566,7 @@ __device__ __forceinline__ void vs_advance(VsSlot<NPR>& sl) {
     sl.rbase = sl.rbase == (kVsRing - 1) * B * DH ? 0 : sl.rbase + B * DH;
 }
 
-template <int LPC, int NPR, bool PAD, int BR, int VG>
+template <int LPC, int NPR, bool PAD, int BR, int VG, bool SAT>
 __global__ void __launch_bounds__(32 * vs_warps<LPC, BR, VG>(), vs_ctas_per_sm<LPC, BR, VG>())
     k_sgbm_vsum(SgbmDims d, SgbmWorkspace ws, size_t ws_stride, int y0, int parity) {
     constexpr int CPW = vs_cpw<LPC>(), B = vs_tile<LPC, VG>(), DH = LPC * NPR, NDG = vs_diag_groups<LPC, BR, VG>(), NWARP = vs_warps<LPC, BR, VG>();
@@ -681,7 +689,7 @@ __global__ void __launch_bounds__(32 * vs_warps<LPC, BR, VG>(), vs_ctas_per_sm<L
         for (int k = 0; k < 2; k++) {
             if (!act[k]) continue;
             if (mine[k]) {
-                vs_meet<LPC, NPR, BR>(sl[k], q, ring, Sv);
+                vs_meet<LPC, NPR, BR, SAT>(sl[k], q, ring, Sv);
                 if (CHECK && t - sl[k].kind == R - 1) {
                     const int xc = x[k] + (sl[k].dcol / DH) * (R - 1);
                     stv<NPR>(bb_out + ((size_t)sl[k].kind * W1 + xc) * DH + q * NPR, sl[k].s.L);
@@ -695,6 +703,8 @@ __global__ void __launch_bounds__(32 * vs_warps<LPC, BR, VG>(), vs_ctas_per_sm<L
     using F = std::false_type;
     int t = 0;
     if (edge) {
+        for (; t < 2 && t < R + 2; t++) iteration(t, T(), T());
+        for (; t < R - 1; t++) iteration(t, F(), T());
         for (; t < R + 2; t++) iteration(t, T(), T());
     } else {
         for (; t < 2 && t < R + 2; t++) iteration(t, T(), F());
@@ -922,7 +932,7 @@ __device__ __forceinline__ void horiz_load_lv(const HorizRow<NPR>& R, ptrdiff_t 
 // One K-cell segment of phase 2.  On entry cb / ckv / lv hold C, the other warp's checkpoint and the vertical sums of
 // segment j (requested one segment earlier); on exit they hold those of segment j-1.  FULL: all K cells exist (only the
 // segment next to the rendezvous can be short).
-template <int NPR, bool PAD, int NV, bool BATCH, int DIRX, bool FULL>
+template <int NPR, bool PAD, int NV, bool BATCH, bool SAT, int DIRX, bool FULL>
 __device__ __forceinline__ void horiz_segment(const SgbmDims& d, const HorizRow<NPR>& R, PathState<NPR>& s, int lane, int j, int cnt,
                                               uint32_t (&cb)[horiz_seg<NPR>()][NPR], uint32_t (&ckv)[NPR],
                                               uint32_t (&lv)[horiz_nreg<NV>()][horiz_seg<NPR>()][NPR], const uint32_t (&padmask)[NPR],
@@ -957,7 +967,7 @@ __device__ __forceinline__ void horiz_segment(const SgbmDims& d, const HorizRow<
 #pragma unroll
                 for (int v = 0; v < horiz_nreg<NV>(); v++)
 #pragma unroll
-                    for (int r = 0; r < NPR; r++) sv[i][r] = __viaddmin_u16x2(sv[i][r], lv[v][i][r], kMaxC2);
+                    for (int r = 0; r < NPR; r++) sv[i][r] = sum16<SAT>(sv[i][r], lv[v][i][r]);
             }
         }
     }
@@ -970,7 +980,7 @@ __device__ __forceinline__ void horiz_segment(const SgbmDims& d, const HorizRow<
                     uint32_t u[NPR];
                     ldv<NPR>(u, R.Lv + (size_t)v * R.vol + o0 - i * DS);
 #pragma unroll
-                    for (int r = 0; r < NPR; r++) sv[i][r] = __viaddmin_u16x2(sv[i][r], u[r], kMaxC2);
+                    for (int r = 0; r < NPR; r++) sv[i][r] = sum16<SAT>(sv[i][r], u[r]);
                 }
             }
         }
@@ -993,7 +1003,7 @@ __device__ __forceinline__ void horiz_segment(const SgbmDims& d, const HorizRow<
             path_step<32, NPR, PAD>(s, cb[i], padmask, P1P1, P2P2, pl);
             uint32_t S[NPR];
 #pragma unroll
-            for (int r = 0; r < NPR; r++) S[r] = __viaddmin_u16x2(sv[i][r], s.L[r], kMaxC2);
+            for (int r = 0; r < NPR; r++) S[r] = sum16<SAT>(sv[i][r], s.L[r]);
             if (batched) stv<NPR>(R.svec + i * WPC + lane * NPR, S);
             else wta_cell<NPR, PAD>(S, lane, d, xo - DIRX * i, R.selA, R.selB, R.selBest);
         }
@@ -1013,7 +1023,7 @@ __device__ __forceinline__ void horiz_segment(const SgbmDims& d, const HorizRow<
     }
 }
 
-template <int NPR, bool PAD, int NV, bool BATCH, int DIRX>
+template <int NPR, bool PAD, int NV, bool BATCH, bool SAT, int DIRX>
 __device__ __forceinline__ void horiz_phase2(const SgbmDims& d, const HorizRow<NPR>& R, PathState<NPR>& s, int lane) {
     constexpr int WPC = 32 * NPR, K = horiz_seg<NPR>(), DS = DIRX * WPC;
     const int n2 = R.n2;
@@ -1037,13 +1047,13 @@ __device__ __forceinline__ void horiz_phase2(const SgbmDims& d, const HorizRow<N
         horiz_load_lv<NPR, NV, DIRX, false>(R, o0, cnt, lv);
     }
     if (cnt < K) {
-        horiz_segment<NPR, PAD, NV, BATCH, DIRX, false>(d, R, s, lane, j, cnt, cb, ckv, lv, padmask, P1P1, P2P2, pl);
+        horiz_segment<NPR, PAD, NV, BATCH, SAT, DIRX, false>(d, R, s, lane, j, cnt, cb, ckv, lv, padmask, P1P1, P2P2, pl);
         j--;
     }
-    for (; j >= 0; j--) horiz_segment<NPR, PAD, NV, BATCH, DIRX, true>(d, R, s, lane, j, K, cb, ckv, lv, padmask, P1P1, P2P2, pl);
+    for (; j >= 0; j--) horiz_segment<NPR, PAD, NV, BATCH, SAT, DIRX, true>(d, R, s, lane, j, K, cb, ckv, lv, padmask, P1P1, P2P2, pl);
 }
 
-template <int NPR, bool PAD, int NV, bool BATCH>
+template <int NPR, bool PAD, int NV, bool BATCH, bool SAT>
 __global__ void __launch_bounds__(64, NPR == 4 ? 6 : OVO_HOR_MINB) k_sgbm_horiz(SgbmDims d, SgbmWorkspace ws, size_t ws_stride) {
     OVO_DYN_SMEM(uint32_t, hsm);
     uint32_t* d2key = hsm;                                        // [W]
@@ -1083,8 +1093,8 @@ __global__ void __launch_bounds__(64, NPR == 4 ? 6 : OVO_HOR_MINB) k_sgbm_horiz(
     if (wid == 0) horiz_phase1<NPR, PAD, 1>(d, R, s, lane);
     else horiz_phase1<NPR, PAD, -1>(d, R, s, lane);
     __syncthreads();
-    if (wid == 0) horiz_phase2<NPR, PAD, NV, BATCH, 1>(d, R, s, lane);
-    else horiz_phase2<NPR, PAD, NV, BATCH, -1>(d, R, s, lane);
+    if (wid == 0) horiz_phase2<NPR, PAD, NV, BATCH, SAT, 1>(d, R, s, lane);
+    else horiz_phase2<NPR, PAD, NV, BATCH, SAT, -1>(d, R, s, lane);
     __syncthreads();
     // ---- uniqueness, sub-pixel refinement and disp2 (A.4.4), data-parallel over the row
     {
@@ -1275,11 +1285,11 @@ static bool use_fused_vertical() {
     return on;
 }
 
-template <int LPC, int NPR, bool PAD, int BR, int VG>
+template <int LPC, int NPR, bool PAD, int BR, int VG, bool SAT>
 int launch_vsum(const SgbmDims& d, const SgbmWorkspace& ws, size_t ws_stride, int nb, cudaStream_t st) {
     constexpr int B = vs_tile<LPC, VG>();
     const size_t smem = ((size_t)kVsRing * B + (size_t)kVsStrips * (B + 2 * BR)) * LPC * NPR * 4 + kVsStrips * 8;
-    auto k_sgbm_vsum_t = k_sgbm_vsum<LPC, NPR, PAD, BR, VG>;
+    auto k_sgbm_vsum_t = k_sgbm_vsum<LPC, NPR, PAD, BR, VG, SAT>;
     if (smem > 48 * 1024) OVO_CUDA(cudaFuncSetAttribute(k_sgbm_vsum_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const dim3 grid(cdiv(d.W1, B), nb), block(32 * vs_warps<LPC, BR, VG>());
     for (int y0 = 0, band = 0; y0 < d.H; y0 += BR, band++) {
@@ -1293,14 +1303,21 @@ template <int NPR, bool PAD>
 int launch_paths(const SgbmDims& d, const SgbmWorkspace& ws, size_t ws_stride, int nb, cudaStream_t st) {
     // the band-state buffer of the fused kernel lives in the second volume: 6 * W1 vectors must fit into two volumes
     const bool fused = d.mode == 0 && d.H >= 4 && use_fused_vertical();
+    // no sum of five path costs can reach MAX_COST: the sums need no saturation (SURVEY.md A.4 bounds C by bs^2 * (2 ftzero + 63))
+    // (padded disparities then hold 5 * 0x7FFF mod 2^16 = 32763 after the sums, still above every real sum: keep a margin)
+    const bool nosat = 5 * (d.bs * d.bs * (2 * d.ftzero + 63) + d.P2) <= 32000;
     if (fused) {
         int rc;
 #ifndef OVO_VS_VG
-#define OVO_VS_VG 8
+#define OVO_VS_VG 16
 #endif
-        if constexpr (NPR == 1) rc = launch_vsum<8, 4, PAD, 16, OVO_VS_VG>(d, ws, ws_stride, nb, st);        // Dp = 64
-        else if constexpr (NPR == 2) rc = launch_vsum<8, 8, PAD, 16, OVO_VS_VG>(d, ws, ws_stride, nb, st);   // Dp = 128
-        else rc = launch_vsum<16, 8, PAD, 8, 16>(d, ws, ws_stride, nb, st);                                  // Dp = 256
+        auto vs = [&](auto sat) -> int {
+            constexpr bool SAT = decltype(sat)::value;
+            if constexpr (NPR == 1) return launch_vsum<8, 4, PAD, 16, OVO_VS_VG, SAT>(d, ws, ws_stride, nb, st);        // Dp = 64
+            else if constexpr (NPR == 2) return launch_vsum<8, 8, PAD, 16, OVO_VS_VG, SAT>(d, ws, ws_stride, nb, st);   // Dp = 128
+            else return launch_vsum<16, 8, PAD, 8, 16, SAT>(d, ws, ws_stride, nb, st);                                  // Dp = 256
+        };
+        rc = nosat ? vs(std::false_type()) : vs(std::true_type());
         if (rc) return rc;
     } else {
         dim3 gv((d.mode ? 6 : 3) * cdiv(d.W1, 8), nb);
@@ -1315,8 +1332,12 @@ int launch_paths(const SgbmDims& d, const SgbmWorkspace& ws, size_t ws_stride, i
         return 0;
     };
     int rc;
-    if (d.uniq < 100) rc = fused ? go(k_sgbm_horiz<NPR, PAD, 1, true>) : (d.mode ? go(k_sgbm_horiz<NPR, PAD, 6, true>) : go(k_sgbm_horiz<NPR, PAD, 3, true>));
-    else rc = fused ? go(k_sgbm_horiz<NPR, PAD, 1, false>) : (d.mode ? go(k_sgbm_horiz<NPR, PAD, 6, false>) : go(k_sgbm_horiz<NPR, PAD, 3, false>));
+    if (d.uniq < 100)
+        rc = fused ? (nosat ? go(k_sgbm_horiz<NPR, PAD, 1, true, false>) : go(k_sgbm_horiz<NPR, PAD, 1, true, true>))
+                   : (d.mode ? go(k_sgbm_horiz<NPR, PAD, 6, true, true>) : go(k_sgbm_horiz<NPR, PAD, 3, true, true>));
+    else
+        rc = fused ? (nosat ? go(k_sgbm_horiz<NPR, PAD, 1, false, false>) : go(k_sgbm_horiz<NPR, PAD, 1, false, true>))
+                   : (d.mode ? go(k_sgbm_horiz<NPR, PAD, 6, false, true>) : go(k_sgbm_horiz<NPR, PAD, 3, false, true>));
     if (rc) return rc;
     OVO_LAUNCH_CHECK();
     return 0;

@@ -36,7 +36,7 @@ def gather_poses(local_T, local_status, mine, n_seq):
     owner [n_seq]) on every rank.
     """
     world, rank = dist.get_world_size(), dist.get_rank()
-    n_frames = local_T.shape[1] if len(mine) else 0
+    n_local = n_frames = local_T.shape[1] if len(mine) else 0
     dev = _device()
     meta = torch.tensor([len(mine), n_frames], dtype=torch.int64, device=dev)
     metas = [torch.zeros_like(meta) for _ in range(world)]
@@ -50,8 +50,11 @@ def gather_poses(local_T, local_status, mine, n_seq):
         buf = np.zeros((cap, 1 + n_frames + n_frames * 16))
         buf[:, 0] = -1
         buf[:k, 0] = mine
-        buf[:k, 1:1 + n_frames] = local_status
-        buf[:k, 1 + n_frames:] = np.asarray(local_T, np.float64).reshape(k, -1)
+        # a rank may hold fewer frames than the longest one: pad with status 0 (frame not committed) / zero transforms
+        buf[:k, 1:1 + n_local] = local_status
+        padded = np.zeros((k, n_frames, 16))
+        padded[:, :n_local] = np.asarray(local_T, np.float64).reshape(k, n_local, 16)
+        buf[:k, 1 + n_frames:] = padded.reshape(k, -1)
         pack = torch.from_numpy(buf.reshape(-1)).to(dev)
     else:
         pack.view(cap, -1)[:, 0] = -1

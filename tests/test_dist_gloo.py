@@ -41,6 +41,13 @@ def _worker(rank, world, port, q):
                     p, c = c, allT[i, j] @ p
             ref.append(c)
         assert np.abs(chains - np.stack(ref)).max() < 1e-12
+        # ragged: rank 1 holds two frames fewer than rank 0 (its missing frames read as "not committed")
+        nf = n_frames - 2 * rank
+        T2, s2, _ = D.gather_poses(allT[mine][:, :nf], status[mine][:, :nf], mine, n_seq)
+        assert T2.shape[1] == n_frames
+        for i in range(n_seq):
+            k = n_frames - 2 * (i % world)
+            assert np.array_equal(T2[i, :k], allT[i, :k]) and np.array_equal(s2[i, :k], status[i, :k]) and not s2[i, k:].any()
         # frame-chunk gather: every rank contributes its contiguous chunk of one sequence
         nfr = 7
         first, start, end = D.shard_frames(nfr, rank, world)
