@@ -11,6 +11,7 @@ HBM; `e2e` is the same loop through the public host-buffer API (numpy frames in 
 read back every step).  Timing: CUDA events around the K steps, barrier + synchronize on both sides, max over ranks.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -163,6 +164,38 @@ def run_cpu_profile(cfg_key, L, R, nframes):
         return {"error": repr(e)}
     finally:
         os.unlink(frames_file)
+
+
+def single_sequence(cam, cfg, pin_L, pin_R, L, R, n_frames=200):
+    """BASELINE configs 1/2: ONE 200-frame KITTI-shaped sequence on one GPU.  `value`: frame-parallel chunks
+    (openvo_b200.sequence.SequenceOdometer.run: host frames in pinned memory -> poses), identical results to the streaming
+    update() loop, which is timed next to it (the latency-bound way a live camera would drive the odometer)."""
+    import torch
+    from openvo_b200 import StereoOdometer
+    from openvo_b200.sequence import SequenceOdometer
+    idx = [frame_index(s, 0) for s in range(n_frames)]
+    lefts, rights = [pin_L[i] for i in idx], [pin_R[i] for i in idx]
+    od = SequenceOdometer(cam, chunk=24, nfeatures=cfg["n"], preprocessed_frames=True)
+    od.run(lefts[:48], rights[:48])  # warm-up: allocations, first launches
+    od = SequenceOdometer(cam, chunk=24, nfeatures=cfg["n"], preprocessed_frames=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    oks = od.run(lefts, rights)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    st = StereoOdometer(cam, nfeatures=cfg["n"], preprocessed_frames=True, _engine_tag=998)
+    for k in range(3):
+        st.update(L[idx[k]], R[idx[k]])
+    st = StereoOdometer(cam, nfeatures=cfg["n"], preprocessed_frames=True, _engine_tag=998)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    want = [st.update(L[i], R[i]) for i in idx]
+    torch.cuda.synchronize()
+    dts = time.perf_counter() - t0
+    return {"workload": "one synthetic %s sequence of %d frames, host frames in, poses out" % (cfg["name"], n_frames),
+            "value": n_frames / dt, "unit": "frames/s", "chunk": 24, "frames_committed": int(sum(oks)),
+            "streaming_update_frames_per_s": n_frames / dts, "streaming_ms_per_frame": 1e3 * dts / n_frames,
+            "identical_to_streaming": bool(oks == want and np.array_equal(od.c_T_w, st.c_T_w) and od.skip_cause == st.skip_cause)}
 
 
 def frame_sharded_4k(rank, world, n_frames=16, n_render=4):
@@ -587,9 +620,13 @@ def main():
         del dev["bos"], e2e["bos"], od0, e2e0
         bos = b0 = eng0 = None
         cam._engines.clear()
-        import gc
         gc.collect()
         torch.cuda.empty_cache()
+        if world == 1 and a.config == "K":
+            extras["single_sequence"] = single_sequence(cam, cfg, pin_L, pin_R, L, R)
+            cam._engines.clear()
+            gc.collect()
+            torch.cuda.empty_cache()
         if world > 1:
             extras["frame_sharded_4k"] = frame_sharded_4k(rank, world)
         elif a.config == "K":

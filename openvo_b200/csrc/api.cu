@@ -146,8 +146,8 @@ struct ovo_ctx {
     uint8_t* filter_scratch;
     uint8_t* pnp_scratch;
     // pinned host staging for the keypoint selection
-    int32_t* h_lvl;    // [max_batch][32]
-    float* h_resp;     // [max_batch][cand_cap][2]
+    int32_t* h_lvl;    // [max_batch][64]
+    float* h_resp;     // [max_batch][cand_cap][2]: first half = FAST scores (bytes), second half = Harris of the survivors
     int32_t* h_sel;    // [max_batch][kp_cap]
     int32_t* h_nsel;   // [max_batch]
     long long h2d_bytes = 0, d2h_bytes = 0;  // staging traffic of the keypoint selection
@@ -251,7 +251,7 @@ ovo_ctx* ovo_create(const ovo_config* cfg, void* workspace_dev, size_t workspace
     orb_make_resize_tables(L.orb, tab.data(), c->L.tab_off, &tot);
     bool ok = cudaMemcpy(c->tab_dev, tab.data(), (size_t)tot * 4, cudaMemcpyHostToDevice) == cudaSuccess;
     const int nb = cfg->max_batch;
-    ok = ok && cudaMallocHost((void**)&c->h_lvl, (size_t)nb * 32 * 4) == cudaSuccess;
+    ok = ok && cudaMallocHost((void**)&c->h_lvl, (size_t)nb * 64 * 4) == cudaSuccess;
     ok = ok && cudaMallocHost((void**)&c->h_resp, (size_t)nb * L.orb.cand_cap * 8) == cudaSuccess;
     ok = ok && cudaMallocHost((void**)&c->h_sel, (size_t)nb * L.orb.kp_cap * 4) == cudaSuccess;
     ok = ok && cudaMallocHost((void**)&c->h_nsel, (size_t)nb * 4) == cudaSuccess;
@@ -328,21 +328,27 @@ int ovo_orb_detect_finish(ovo_ctx* c, int nb, float* kp, uint8_t* desc, int* n_k
     const Layout& L = c->L;
     const OrbDims& d = L.orb;
     for (int f = 0; f < nb; f++)
-        OVO_CUDA(cudaMemcpyAsync(c->h_lvl + 32 * f, (uint8_t*)c->orb0.lvl_count + L.frame_bytes * f, 17 * 4, cudaMemcpyDeviceToHost, st));
+        OVO_CUDA(cudaMemcpyAsync(c->h_lvl + 64 * f, (uint8_t*)c->orb0.lvl_count + L.frame_bytes * f, 34 * 4, cudaMemcpyDeviceToHost, st));
     OVO_CUDA(cudaStreamSynchronize(st));
-    c->d2h_bytes += 17 * 4 * (long long)nb;
+    c->d2h_bytes += 34 * 4 * (long long)nb;
     for (int f = 0; f < nb; f++) {
-        const int total = c->h_lvl[32 * f + 16];
+        const int total = c->h_lvl[64 * f + 16], surv = c->h_lvl[64 * f + 33];
         if (total > d.cand_cap) { set_error("ORB candidate overflow (%d > %d)", total, d.cand_cap); return 1; }
-        c->d2h_bytes += (long long)total * 8;
+        // the 8-bit FAST score of every candidate (the introselect permutation depends on the whole array) and the Harris
+        // response of the first pass's survivors only
+        c->d2h_bytes += (long long)total + (long long)surv * 4;
+        uint8_t* hs = (uint8_t*)(c->h_resp + (size_t)f * d.cand_cap * 2);
+        float* hh = c->h_resp + (size_t)f * d.cand_cap * 2 + d.cand_cap;
         if (total > 0)
-            OVO_CUDA(cudaMemcpyAsync(c->h_resp + (size_t)f * d.cand_cap * 2, (uint8_t*)c->orb0.cand_resp + L.frame_bytes * f,
-                                     (size_t)total * 8, cudaMemcpyDeviceToHost, st));
+            OVO_CUDA(cudaMemcpyAsync(hs, (uint8_t*)c->orb0.cand_score + L.frame_bytes * f, (size_t)total, cudaMemcpyDeviceToHost, st));
+        if (surv > 0)
+            OVO_CUDA(cudaMemcpyAsync(hh, (uint8_t*)c->orb0.harris_dense + L.frame_bytes * f, (size_t)surv * 4, cudaMemcpyDeviceToHost, st));
     }
     OVO_CUDA(cudaStreamSynchronize(st));
     // retainBest x2 per level on the host (DESIGN.md "retainBest"); frames are independent -> one thread each
     auto select_one = [&](int f) {
-        c->h_nsel[f] = orb_host_select(d, c->h_lvl + 32 * f, c->h_resp + (size_t)f * d.cand_cap * 2, c->h_sel + (size_t)f * d.kp_cap);
+        c->h_nsel[f] = orb_host_select(d, c->h_lvl + 64 * f, (const uint8_t*)(c->h_resp + (size_t)f * d.cand_cap * 2),
+                                       c->h_resp + (size_t)f * d.cand_cap * 2 + d.cand_cap, c->h_sel + (size_t)f * d.kp_cap);
     };
     static const int max_threads = [] {
         const char* e = getenv("OVO_SELECT_THREADS");   // host threads used for the per-frame retainBest emulation (default 4)
@@ -360,6 +366,7 @@ int ovo_orb_detect_finish(ovo_ctx* c, int nb, float* kp, uint8_t* desc, int* n_k
     }
     int max_sel = 0;
     for (int f = 0; f < nb; f++) {
+        if (c->h_nsel[f] == -2) { set_error("ORB: the device's survivor set disagrees with the host selection (internal error)"); return 1; }
         if (c->h_nsel[f] < 0) { set_error("ORB keypoint capacity exceeded (ties at the retainBest boundary)"); return 1; }
         n_kp_host[f] = c->h_nsel[f];
         max_sel = c->h_nsel[f] > max_sel ? c->h_nsel[f] : max_sel;

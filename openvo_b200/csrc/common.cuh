@@ -88,16 +88,22 @@ struct OrbWorkspace {           // per frame, device pointers
     uint8_t *pyr, *maskpyr, *score, *blur;  // [total_px] each
     int32_t* row_offset;                     // [total_rows] candidates before the row, over all levels
     uint32_t* candmask;                      // [total_mwords] one bit per pixel: NMS + border + mask survivor
-    int32_t* lvl_count;                      // [8] candidates per level (+ [8] offsets)
+    int32_t* lvl_count;                      // [64]: [0..7] candidates per level, [8..15] level offsets, [16] total; survivors of the
+                                             // first retainBest (FAST score >= the level's boundary score): [17..24] per level,
+                                             // [25..32] offsets, [33] total
     int32_t* cand_xy;                        // [cand_cap] packed (y<<16 | x)
-    float* cand_resp;                        // [cand_cap][2] (FAST score, Harris response)
+    uint8_t* cand_score;                     // [cand_cap] FAST score
+    float* cand_harris;                      // [cand_cap] Harris response (written for survivors only)
+    float* harris_dense;                     // [cand_cap] Harris responses of the survivors, in candidate order (what the host reads)
+    int32_t* surv_id;                        // [cand_cap] candidate ids of the survivors, in candidate order
     int32_t* sel;                            // [kp_cap] selected candidate ids (level-major, final order)
 };
 size_t orb_workspace_bytes(const OrbDims& d);
 void orb_carve(const OrbDims& d, uint8_t* base, OrbWorkspace* ws);
 // host-side exact KeyPointsFilter::retainBest emulation (libstdc++ introselect order), host_select.cpp
-// cand_resp: [n][2]; lvl_count: [8]; out_sel: [kp_cap]; returns number selected (or -1 on overflow)
-int orb_host_select(const OrbDims& d, const int32_t* lvl_count, const float* cand_resp, int32_t* out_sel);
+// lvl_count: [64] as above; scores: FAST score of every candidate; harris_dense: Harris response of the survivors;
+// out_sel: [kp_cap]; returns number selected (-1 on capacity overflow, -2 if the device's survivor set disagrees)
+int orb_host_select(const OrbDims& d, const int32_t* lvl_count, const uint8_t* scores, const float* harris_dense, int32_t* out_sel);
 
 // ---- matcher / pose ----------------------------------------------------------------------------------------
 // nn_out [nq][4] = (idx0, d0, idx1, d1), ties -> lowest train index

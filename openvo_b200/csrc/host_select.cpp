@@ -36,17 +36,33 @@ void retain_best(std::vector<Rec>& k, int n) {
 }
 }  // namespace
 
-// lvl_count: [17] as written by k_orb_scan (per-level counts, per-level offsets, total); cand_resp: [n][2] =
-// (FAST score, Harris response) in raster order per level.  out_sel receives candidate ids in final keypoint order.
-int orb_host_select(const OrbDims& d, const int32_t* lvl_count, const float* cand_resp, int32_t* out_sel) {
+// lvl_count: [64] as written by k_orb_scan / k_orb_survivors (per-level candidate counts and offsets, total; per-level
+// survivor counts and offsets, total); scores: FAST score of every candidate in raster order per level; harris_dense: Harris
+// response of the survivors of the first pass (the candidates whose score reaches the level's boundary score), in candidate
+// order — the device finds that SET with a histogram, so only the survivors' responses are computed and shipped; the ORDER
+// of the survivors is produced here.  out_sel receives candidate ids in final keypoint order.
+int orb_host_select(const OrbDims& d, const int32_t* lvl_count, const uint8_t* scores, const float* harris_dense, int32_t* out_sel) {
     int n_out = 0;
     std::vector<Rec> k;
+    std::vector<int32_t> dense;
     for (int l = 0; l < ORB_NLEVELS; l++) {
         const int n = lvl_count[l], base = lvl_count[ORB_NLEVELS + l];
         k.resize(n);
-        for (int i = 0; i < n; i++) k[i] = {cand_resp[2 * (size_t)(base + i)], base + i};
+        for (int i = 0; i < n; i++) k[i] = {(float)scores[base + i], base + i};
         retain_best(k, 2 * d.lv[l].nfeat);
-        for (auto& r : k) r.resp = cand_resp[2 * (size_t)r.id + 1];
+        // survivors = every candidate with score >= the boundary score (retainBest keeps all ties); the device numbered them in
+        // candidate order
+        float amb = 0.f;
+        if ((int)k.size() < n) {
+            amb = 256.f;
+            for (auto& r : k) amb = std::min(amb, r.resp);
+        }
+        dense.assign(n, -1);
+        int j = lvl_count[25 + l];
+        for (int i = 0; i < n; i++)
+            if ((float)scores[base + i] >= amb) dense[i] = j++;
+        if (j - lvl_count[25 + l] != lvl_count[17 + l] || lvl_count[17 + l] != (int)k.size()) return -2;
+        for (auto& r : k) r.resp = harris_dense[dense[r.id - base]];
         retain_best(k, d.lv[l].nfeat);
         if (n_out + (int)k.size() > d.kp_cap) return -1;
         for (auto& r : k) out_sel[n_out++] = r.id;

@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(256) k_orb_emit(OrbDims d, OrbWorkspace ws, si
     const uint32_t* w = fptr(ws.candmask, ws_stride, f) + L.moff + (size_t)y * L.mw;
     const uint8_t* sc = fptr(ws.score, ws_stride, f) + L.off + (size_t)y * L.w;
     int32_t* cxy = fptr(ws.cand_xy, ws_stride, f);
-    float* cresp = fptr(ws.cand_resp, ws_stride, f);
+    uint8_t* cscore = fptr(ws.cand_score, ws_stride, f);
     int base = fptr(ws.row_offset, ws_stride, f)[r];
     for (int i0 = 0; i0 < L.mw; i0 += 32) {
         uint32_t bits = i0 + lane < L.mw ? w[i0 + lane] : 0u;
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(256) k_orb_emit(OrbDims d, OrbWorkspace ws, si
             const int x = (i0 + lane) * 32 + b;
             if (idx < d.cand_cap) {
                 cxy[idx] = (y << 16) | x;
-                cresp[2 * idx] = (float)sc[x];
+                cscore[idx] = sc[x];
             }
             idx++;
         }
@@ -291,12 +291,80 @@ __device__ __forceinline__ int cand_level(const int32_t* lvl, int i) {
     return l;
 }
 
-// ---- Harris response of every candidate (A.1.6) ---------------------------------------------------------------------------
+// ---- survivors of the first retainBest pass (A.1.5) -----------------------------------------------------------------------
+// KeyPointsFilter::retainBest(2 * n_l) on the FAST score keeps every candidate whose score reaches the (2 n_l)-th largest one
+// (all ties at the boundary stay).  That SET needs no ordering: a 256-bin histogram of the 8-bit scores gives the boundary,
+// an ordered compaction the survivors' ids.  Only they get a Harris response, and only their responses travel to the host,
+// which still produces the survivors' ORDER (libstdc++'s introselect permutation, host_select.cpp).  One CTA per frame.
+__global__ void __launch_bounds__(1024) k_orb_survivors(OrbDims d, OrbWorkspace ws, size_t ws_stride) {
+    __shared__ int hist[256];
+    __shared__ int warp_sums[32];
+    __shared__ int s_amb, s_base;
+    const int f = blockIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int32_t* lvl = fptr(ws.lvl_count, ws_stride, f);
+    const uint8_t* score = fptr(ws.cand_score, ws_stride, f);
+    int32_t* surv = fptr(ws.surv_id, ws_stride, f);
+    if (threadIdx.x == 0) s_base = 0;
+    for (int l = 0; l < ORB_NLEVELS; l++) {
+        const int n = min(lvl[l], max(d.cand_cap - lvl[ORB_NLEVELS + l], 0)), base = lvl[ORB_NLEVELS + l], keep = 2 * d.lv[l].nfeat;
+        if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+        __syncthreads();
+        if (n > keep && keep > 0)
+            for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&hist[score[base + i]], 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int amb = 0;                      // n <= keep: nothing is cut
+            if (keep == 0) amb = 256;         // retainBest(0): nothing survives
+            else if (n > keep) {
+                int acc = 0;
+                for (amb = 255; amb > 0; amb--) {
+                    acc += hist[amb];
+                    if (acc >= keep) break;
+                }
+            }
+            s_amb = amb;
+        }
+        __syncthreads();
+        const int amb = s_amb, out0 = s_base;
+        int done = 0;  // survivors of the chunks before this one
+        for (int i0 = 0; i0 < n; i0 += 1024) {
+            const int i = i0 + threadIdx.x;
+            const bool p = i < n && (int)score[base + i] >= amb;
+            const uint32_t bal = __ballot_sync(0xffffffffu, p);
+            if (lane == 0) warp_sums[wid] = __popc(bal);
+            __syncthreads();
+            if (wid == 0) {
+                int s = warp_sums[lane];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, s, o);
+                    if (lane >= o) s += t;
+                }
+                warp_sums[lane] = s;
+            }
+            __syncthreads();
+            if (p) surv[out0 + done + (wid ? warp_sums[wid - 1] : 0) + __popc(bal & ((1u << lane) - 1))] = base + i;
+            done += warp_sums[31];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            lvl[17 + l] = done;
+            lvl[25 + l] = out0;
+            s_base = out0 + done;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) lvl[33] = s_base;
+}
+
+// ---- Harris response of the survivors (A.1.6) ------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_orb_harris(OrbDims d, OrbWorkspace ws, size_t ws_stride) {
     const int f = blockIdx.y;
     const int32_t* lvl = fptr(ws.lvl_count, ws_stride, f);
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= min(lvl[2 * ORB_NLEVELS], d.cand_cap)) return;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= lvl[33]) return;
+    const int i = fptr(ws.surv_id, ws_stride, f)[j];
     const OrbLevel L = d.lv[cand_level(lvl, i)];
     const uint8_t* img = fptr(ws.pyr, ws_stride, f) + L.off;
     const int xy = fptr(ws.cand_xy, ws_stride, f)[i];
@@ -330,7 +398,8 @@ __global__ void __launch_bounds__(128) k_orb_harris(OrbDims d, OrbWorkspace ws, 
     const float det = __fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc));
     const float tr = __fadd_rn(fa, fb);
     const float resp = __fmul_rn(__fsub_rn(det, __fmul_rn(__fmul_rn(0.04f, tr), tr)), s4);
-    fptr(ws.cand_resp, ws_stride, f)[2 * i + 1] = resp;
+    fptr(ws.cand_harris, ws_stride, f)[i] = resp;
+    fptr(ws.harris_dense, ws_stride, f)[j] = resp;
 }
 
 // ---- float32 separable Gaussian with the AVX2 engine's body / tail split (A.2.1) -------------------------------------------
@@ -482,7 +551,7 @@ __global__ void __launch_bounds__(128) k_orb_describe(OrbDims d, OrbWorkspace ws
     if (lane == 0) {
         float* o = kp_out + ((size_t)f * d.kp_cap + k) * 6;
         o[0] = ptx; o[1] = pty; o[2] = __fmul_rn(31.f, L.scale); o[3] = angle;
-        o[4] = fptr(ws.cand_resp, ws_stride, f)[2 * ci + 1];
+        o[4] = fptr(ws.cand_harris, ws_stride, f)[ci];
         o[5] = (float)level;
     }
     // rBRIEF (A.2.2): lane i produces descriptor byte i
@@ -552,8 +621,8 @@ size_t orb_workspace_bytes(const OrbDims& d) {
     b += 4 * align_up((size_t)d.total_px + 64, 256);
     b += align_up((size_t)d.total_rows * 4, 256);
     b += align_up((size_t)d.total_mwords * 4, 256);
-    b += align_up(32 * 4, 256);
-    b += align_up((size_t)d.cand_cap * 4, 256) + align_up((size_t)d.cand_cap * 8, 256);
+    b += align_up(64 * 4, 256);
+    b += 4 * align_up((size_t)d.cand_cap * 4, 256) + align_up((size_t)d.cand_cap, 256);
     b += align_up((size_t)d.kp_cap * 4, 256);
     return b;
 }
@@ -567,9 +636,12 @@ void orb_carve(const OrbDims& d, uint8_t* base, OrbWorkspace* ws) {
     ws->blur = p; p += px;
     ws->row_offset = (int32_t*)p; p += align_up((size_t)d.total_rows * 4, 256);
     ws->candmask = (uint32_t*)p; p += align_up((size_t)d.total_mwords * 4, 256);
-    ws->lvl_count = (int32_t*)p; p += align_up(32 * 4, 256);
+    ws->lvl_count = (int32_t*)p; p += align_up(64 * 4, 256);
     ws->cand_xy = (int32_t*)p; p += align_up((size_t)d.cand_cap * 4, 256);
-    ws->cand_resp = (float*)p; p += align_up((size_t)d.cand_cap * 8, 256);
+    ws->cand_harris = (float*)p; p += align_up((size_t)d.cand_cap * 4, 256);
+    ws->harris_dense = (float*)p; p += align_up((size_t)d.cand_cap * 4, 256);
+    ws->surv_id = (int32_t*)p; p += align_up((size_t)d.cand_cap * 4, 256);
+    ws->cand_score = p; p += align_up((size_t)d.cand_cap, 256);
     ws->sel = (int32_t*)p; p += align_up((size_t)d.kp_cap * 4, 256);
 }
 
@@ -619,6 +691,8 @@ int orb_phase1_launch(const OrbDims& d, const OrbWorkspace* ws0, size_t ws_strid
         OVO_LAUNCH_CHECK();
     }
     {
+        OVO_LAUNCH(k_orb_survivors, dim3(nb), dim3(1024), 0, st, d, ws, ws_stride);
+        OVO_LAUNCH_CHECK();
         dim3 grid(cdiv(d.cand_cap, 128), nb);
         OVO_LAUNCH(k_orb_harris, grid, dim3(128), 0, st, d, ws, ws_stride);
         OVO_LAUNCH_CHECK();
