@@ -36,6 +36,20 @@ class NativeError(RuntimeError):
     pass
 
 
+def cv2_error(msg):
+    """The reference's hard input errors surface as cv2.error (an OpenCV C++ assertion); ours are raised as a
+    class that IS a cv2.error (so callers written against the reference keep working) and also a ValueError."""
+    try:
+        import cv2
+        cls = cv2_error.__dict__.get("cls")
+        if cls is None:
+            cls = type("InputError", (cv2.error, ValueError), {})
+            cv2_error.cls = cls
+        return cls(msg)
+    except Exception:
+        return ValueError(msg)
+
+
 _vp, _i, _sz, _d = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_double
 _SIGNATURES = {
     "ovo_last_error": (ctypes.c_char_p, []),

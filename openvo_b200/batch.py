@@ -51,9 +51,18 @@ class BatchOdometer:
                 queued.append(i)
         eng.pair_batch_async(jobs, self.odometers[0].match_threshold, self.odometers[0].cross_check)
         res = eng.pair_collect(self.n) if queued else []
-        out = []
+        out, errors = [], []
         for i, (od, fr) in enumerate(zip(self.odometers, frames)):
-            out.append(od._advance(fr, first=(i, res[i]) if i in queued else None))
+            # a hard failure of one sequence (the reference's ZeroDivisionError / IndexError paths) must not leave the state
+            # machines of the others un-advanced: collect, advance everyone, then re-raise the first
+            try:
+                out.append(od._advance(fr, first=(i, res[i]) if i in queued else None))
+            except (ZeroDivisionError, IndexError) as e:
+                out.append(False)
+                errors.append((i, e))
+        if errors:
+            self.failed = errors
+            raise errors[0][1]
         return out
 
     def poses(self):

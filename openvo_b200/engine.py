@@ -13,14 +13,19 @@ from . import _native as N
 class Frame:
     """Device-resident products of one stereo pair (what the reference keeps in current_*/prev_*,
     ref: src/openVO/stereo_odometer.py:107-113)."""
-    __slots__ = ("img", "disp", "kp", "desc", "n_kp", "_host")
+    __slots__ = ("img", "disp", "kp", "desc", "n_kp", "_host", "_dirty")
 
     def __init__(self, img, disp, kp, desc, n_kp):
         self.img, self.disp, self.kp, self.desc, self.n_kp = img, disp, kp, desc, n_kp
-        self._host = {}
+        self._host = {}      # host-side copies in the reference's types, materialised on first read (or assigned by the caller)
+        self._dirty = False  # host-side products were assigned: the device copy must be rebuilt before the next pair step
 
 
 class Engine:
+    """One engine = one C-ABI context + workspace + pinned staging.  An engine is NOT re-entrant: its staging buffers and its
+    workspace are reused by every call, so it must be driven from one host thread on one CUDA stream at a time (StereoCamera
+    hands out one engine per (nfeatures, batch, tag); drivers that want concurrency use distinct tags, as bench.py does)."""
+
     def __init__(self, width, height, sgbm_params, roi, Q, nfeatures, max_batch=1, min_valid=4.0, max_valid=100.0,
                  device=None, lib_path=None):
         if not torch.cuda.is_available():

@@ -24,10 +24,10 @@ class _SgbmHandle:
         cam = self._cam
         left, right = np.asarray(left), np.asarray(right)
         if left.shape != right.shape or left.dtype != np.uint8 or right.dtype != np.uint8 or left.ndim != 2:
-            raise ValueError("StereoSGBM.compute: left and right must be 2-D uint8 images of equal size "
-                             "(the reference raises cv2.error here)")
+            raise N.cv2_error("StereoSGBM.compute: left and right must be 2-D uint8 images of equal size "
+                              "(OpenCV: left.size() == right.size() && left.type() == right.type())")
         if left.shape != (cam.img_size[1], cam.img_size[0]):
-            raise ValueError("StereoSGBM.compute: image size differs from the camera's img_size")
+            raise N.cv2_error("StereoSGBM.compute: image size differs from the camera's img_size")
         eng = cam.engine()
         l, r = eng.upload(left[None], "sgbm_l"), eng.upload(right[None], "sgbm_r")
         return eng.sgbm(l, r)[0].cpu().numpy()
@@ -97,8 +97,8 @@ class StereoCamera:
         img = np.asarray(img)
         self._check(img)
         if img.ndim == 3:
-            raise ValueError("cv2.remap keeps the channel count; the hot path only rectifies single-channel images "
-                             "(compute_3d converts colour input to gray first, like the reference)")
+            raise N.cv2_error("cv2.remap keeps the channel count; the hot path only rectifies single-channel images "
+                              "(compute_3d converts colour input to gray first, like the reference)")
         eng = self.engine()
         return eng.rectify(eng.upload(img[None], "rect_" + side), self._maps(eng, side))[0].cpu().numpy()
 
@@ -114,13 +114,13 @@ class StereoCamera:
         if hasattr(img, "data_ptr"):  # torch CPU tensor
             import torch
             if img.dtype != torch.uint8 or img.device.type != "cpu" or not img.is_contiguous():
-                raise ValueError("torch frames must be contiguous uint8 CPU (ideally pinned) tensors")
+                raise N.cv2_error("torch frames must be contiguous uint8 CPU (ideally pinned) tensors")
         elif img.dtype != np.uint8:
-            raise ValueError("images must be uint8 (the reference raises cv2.error here)")
+            raise N.cv2_error("images must be uint8")
         if len(img.shape) not in (2, 3) or (len(img.shape) == 3 and img.shape[2] != 3):
-            raise ValueError("images must be uint8, HxW (gray) or HxWx3 (BGR) (the reference raises cv2.error here)")
+            raise N.cv2_error("images must be uint8, HxW (gray) or HxWx3 (BGR)")
         if tuple(img.shape[:2]) != (self.img_size[1], self.img_size[0]):
-            raise ValueError("image size differs from the camera's img_size")
+            raise N.cv2_error("image size differs from the camera's img_size")
 
     def _prepare_device(self, eng, img_left, img_right, preprocessed, key="prep"):
         """Host frames ([H,W] / [H,W,3], or batches [S,H,W] / [S,H,W,3]) -> rectified gray device tensors [S,H,W]
@@ -143,7 +143,7 @@ class StereoCamera:
                 dev = eng.rectify(dev, None if preprocessed else self._maps(eng, side))
             out.append(dev)
         if out[0].shape != out[1].shape:
-            raise ValueError("left and right must be of equal size (the reference raises cv2.error here)")
+            raise N.cv2_error("left and right must be of equal size")
         return out[0], out[1]
 
     def compute_3d(self, img_left, img_right, preprocessed=False):

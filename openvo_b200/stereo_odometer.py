@@ -26,13 +26,13 @@ class _OrbHandle:
         eng = self._od._engine()
         image = np.asarray(image)
         if image.dtype != np.uint8 or image.shape != (eng.ch, eng.cw):
-            raise ValueError("ORB: expected a uint8 image of the camera's cropped size %dx%d" % (eng.cw, eng.ch))
+            raise N.cv2_error("ORB: expected a uint8 image of the camera's cropped size %dx%d" % (eng.cw, eng.ch))
         img = eng.upload(image[None], "orb_img")
         m = None
         if mask is not None:
             mask = np.asarray(mask)
             if mask.dtype != np.uint8 or mask.shape != image.shape:
-                raise ValueError("ORB: mask must be uint8 and of the image's size")
+                raise N.cv2_error("ORB: mask must be uint8 and of the image's size")
             m = eng.upload(mask[None], "orb_mask")
         kp, desc, n = eng.orb(img, m)
         if n[0] == 0:
@@ -95,6 +95,10 @@ class StereoOdometer:
         # opt-in extension (north-star stage 5): "pnp_ransac" = batched P3P RANSAC + LM instead of the reference's Umeyama alignment
         if pose_method not in ("umeyama", "pnp_ransac"):
             raise ValueError("pose_method must be 'umeyama' (the reference's behaviour) or 'pnp_ransac'")
+        if pose_method == "pnp_ransac" and (rigidity_threshold > 0 or outlier_threshold > 0):
+            import warnings
+            warnings.warn("pose_method='pnp_ransac' is ignored while rigidity_threshold / outlier_threshold are set: the filtered "
+                          "path ends in the reference's Umeyama alignment (ref: src/openVO/stereo_odometer.py:177-205)")
         self.pose_method, self.ransac_iters = pose_method, ransac_iters
         self.ransac_reproj_px, self.ransac_seed = ransac_reproj_px, ransac_seed
         self.skipped_frames = 0
@@ -114,6 +118,8 @@ class StereoOdometer:
             return None
         h = frame._host
         if what not in h:
+            if frame.disp is None and what != "kps":   # a frame assembled from caller-assigned products only
+                return None
             if what == "img":
                 h[what] = frame.img.cpu().numpy()
             elif what == "disparity":
@@ -128,16 +134,69 @@ class StereoOdometer:
                 h[what] = frame.desc[:frame.n_kp].cpu().numpy()
         return h[what]
 
-    current_img = property(lambda self: self._host(self._cur, "img"))
-    current_disparity = property(lambda self: self._host(self._cur, "disparity"))
-    current_3d = property(lambda self: self._host(self._cur, "3d"))
-    current_kps = property(lambda self: self._host(self._cur, "kps"))
-    current_desc = property(lambda self: self._host(self._cur, "desc"))
-    prev_img = property(lambda self: self._host(self._prev, "img"))
-    prev_disparity = property(lambda self: self._host(self._prev, "disparity"))
-    prev_3d = property(lambda self: self._host(self._prev, "3d"))
-    prev_kps = property(lambda self: self._host(self._prev, "kps"))
-    prev_desc = property(lambda self: self._host(self._prev, "desc"))
+    # The reference keeps these as plain attributes (ref: src/openVO/stereo_odometer.py:24-31,107-113): readable AND assignable.
+    # Reading materialises the device-resident product on the host (cached); assigning replaces the product, and the device
+    # copy is rebuilt from the host value before the frame is next used for matching.
+    def _state_property(which, what):
+        def get(self):
+            return self._host(getattr(self, which), what)
+
+        def put(self, value):
+            frame = getattr(self, which)
+            if value is None:
+                if what == "img":            # the reference tests `current_img is None` / `prev_img is None` for "no frame yet"
+                    setattr(self, which, None)
+                return
+            if frame is None:
+                from .engine import Frame
+                frame = Frame(None, None, None, None, 0)
+                setattr(self, which, frame)
+            frame._host[what] = value
+            if what == "kps":
+                frame._host.pop("kp_array", None)
+            frame._dirty = True
+        return property(get, put)
+
+    current_img = _state_property("_cur", "img")
+    current_disparity = _state_property("_cur", "disparity")
+    current_3d = _state_property("_cur", "3d")
+    current_kps = _state_property("_cur", "kps")
+    current_desc = _state_property("_cur", "desc")
+    prev_img = _state_property("_prev", "img")
+    prev_disparity = _state_property("_prev", "disparity")
+    prev_3d = _state_property("_prev", "3d")
+    prev_kps = _state_property("_prev", "kps")
+    prev_desc = _state_property("_prev", "desc")
+    del _state_property
+
+    def _device_frame(self, frame):
+        """Rebuild the device copy of a frame whose host-side products were assigned by the caller."""
+        if not getattr(frame, "_dirty", False):
+            return frame
+        import torch
+        eng = self._engine()
+        h = frame._host
+        dev = eng.device
+        if "img" in h:
+            frame.img = torch.from_numpy(np.ascontiguousarray(h["img"], np.uint8)).to(dev)
+        if "disparity" in h:
+            frame.disp = torch.from_numpy(np.ascontiguousarray(h["disparity"], np.float32)).to(dev)
+        if "kps" in h or "kp_array" in h:
+            arr = h.get("kp_array")
+            if arr is None:
+                arr = np.array([[k.pt[0], k.pt[1], k.size, k.angle, k.response, k.octave] for k in h["kps"]], np.float32).reshape(-1, 6)
+            if len(arr) > eng.kp_cap:
+                raise N.cv2_error("more keypoints than the odometer's capacity")
+            kp = torch.zeros((eng.kp_cap, N.KP_FIELDS), dtype=torch.float32, device=dev)
+            kp[:len(arr)] = torch.from_numpy(np.ascontiguousarray(arr, np.float32)).to(dev)
+            frame.kp, frame.n_kp = kp, len(arr)
+        if "desc" in h and h["desc"] is not None:
+            dsc = np.ascontiguousarray(h["desc"], np.uint8)
+            desc = torch.zeros((eng.kp_cap, 32), dtype=torch.uint8, device=dev)
+            desc[:len(dsc)] = torch.from_numpy(dsc).to(dev)
+            frame.desc = desc
+        frame._dirty = False
+        return frame
 
     # ---- helpers that are part of the reference's method surface --------------------------------------------------------
     def feature_mask(self, disparity):
@@ -166,13 +225,71 @@ class StereoOdometer:
                 den = den + wt
         return num / den
 
-    def save_frame_update(self, frame):
-        # ref: src/openVO/stereo_odometer.py:107-113
+    def save_frame_update(self, next_img, next_disp=None, next_3d=None, next_kps=None, next_desc=None):
+        """ref: src/openVO/stereo_odometer.py:107-113 — same five arguments (host products of the next frame): the current
+        frame becomes the previous one, the given products the current one.  (The per-frame path commits its device-resident
+        frame through the same rotation, without materialising anything on the host.)"""
+        from .engine import Frame
+        if isinstance(next_img, Frame):
+            frame = next_img
+        else:
+            frame = Frame(None, None, None, None, 0)
+            frame._host.update({"img": next_img, "disparity": next_disp, "3d": next_3d, "kps": tuple(next_kps), "desc": next_desc})
+            frame._dirty = True
         self._prev, self._cur = self._cur, frame
+
+    def _hooks_overridden(self):
+        # the reference dispatches these through `self.`: a subclass (or instance) override must take effect in update()
+        base = StereoOdometer
+        return any(getattr(type(self), n) is not getattr(base, n) or n in self.__dict__
+                   for n in ("feature_mask", "point_clouds", "point_cloud_transform", "bilinear_interpolate_pixels", "rigid_body_filter",
+                             "save_frame_update"))
+
+    def _update_through_hooks(self, img_left, img_right):
+        """update() exactly as the reference writes it (ref: src/openVO/stereo_odometer.py:115-160), every step dispatched
+        through `self.` on host-side products: used when a subclass overrides one of the steps.  Each step still runs on the
+        device (compute_3d, ORB, knnMatch, estimateAffine3D are the C-ABI seams); only the glue is host Python."""
+        next_3d, next_disp, next_img = self.stereo.compute_3d(img_left, img_right, preprocessed=self.preprocessed_frames)
+        next_kps, next_desc = self.orb.detectAndCompute(next_img, self.feature_mask(next_disp))
+        if len(next_kps) < self.min_matches:
+            self.skipped_frames += 1
+            self.skip_cause = "keypoints"
+            return False
+        if self.current_img is None:
+            self.save_frame_update(next_img, next_disp, next_3d, next_kps, next_desc)
+            return True
+        T = None
+        current_pts, next_pts = self.point_clouds(self.current_kps, next_kps, self.current_desc, next_desc, self.current_3d, next_3d)
+        if current_pts is None:
+            self.skip_cause = "matches"
+        else:
+            T = self.point_cloud_transform(current_pts, next_pts)
+            if T is not None:
+                self.c_T_w_prev = self.c_T_w
+                self.c_T_w = T @ self.c_T_w
+        if T is None and self.prev_img is not None:
+            prev_pts, next_pts = self.point_clouds(self.prev_kps, next_kps, self.prev_desc, next_desc, self.prev_3d, next_3d)
+            if prev_pts is None:
+                self.skip_cause = "matches"
+            else:
+                T = self.point_cloud_transform(prev_pts, next_pts)
+                if T is not None:
+                    T_prev = self.c_T_w_prev
+                    self.c_T_w_prev = self.c_T_w
+                    self.c_T_w = T @ T_prev
+                    self.skipped_frames = 0
+        if T is None:
+            self.skipped_frames += 1
+            return False
+        self.skipped_frames = 0
+        self.save_frame_update(next_img, next_disp, next_3d, next_kps, next_desc)
+        return True
 
     # ---- the per-frame call --------------------------------------------------------------------------------------------------
     def update(self, img_left, img_right):
         """ref: src/openVO/stereo_odometer.py:115-160."""
+        if self._hooks_overridden():
+            return self._update_through_hooks(img_left, img_right)
         eng = self._engine()
         left, right = self.stereo._prepare_device(eng, img_left, img_right, self.preprocessed_frames, key="upd")
         frame = eng.frames(left, right)[0]
@@ -213,6 +330,7 @@ class StereoOdometer:
     def _relative(self, a, b, result=None):
         """point_clouds + point_cloud_transform for device frames a -> b."""
         eng = self._engine()
+        a, b = self._device_frame(a), self._device_frame(b)
         if b.n_kp < 2:
             raise IndexError("tuple index out of range")  # the reference indexes m[1] (ref: stereo_odometer.py:164)
         slot = 0

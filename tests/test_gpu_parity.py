@@ -429,3 +429,60 @@ def test_reference_error_behaviour():
     od.min_matches = 1
     with pytest.raises(IndexError):
         od._relative(good, one)
+
+
+def test_reference_method_surface(golden):
+    """Drop-in details of the reference's class API (ref: src/openVO/stereo_odometer.py:24-31,107-160): update() dispatches
+    its steps through `self.` (subclass overrides take effect), save_frame_update takes the reference's five arguments,
+    current_* / prev_* are assignable, and malformed input raises cv2.error."""
+    import cv2
+    g = golden("seq_small")
+    W, H, D, n = int(g["W"]), int(g["H"]), int(g["D"]), int(g["nfeatures"])
+    cam, _ = _cam(W, H, D)
+
+    calls = []
+
+    class Hooked(StereoOdometer):
+        def point_clouds(self, *a):
+            calls.append("point_clouds")
+            return super().point_clouds(*a)
+
+        def point_cloud_transform(self, p, q):
+            calls.append("transform")
+            return super().point_cloud_transform(p, q)
+
+    # the hooked path (host glue, device seams) reproduces the reference's record like the fused path does
+    od = Hooked(cam, nfeatures=n, preprocessed_frames=True)
+    for i in range(len(g["left"])):
+        assert od.update(g["left"][i], g["right"][i]) == bool(g["ok_%d" % i])
+        assert od.skip_cause == str(g["cause_%d" % i])
+        assert np.array_equal(np.rint(od.current_disparity * 16).astype(np.int16), g["disp16_%d" % i])
+        assert np.array_equal(od.current_desc, g["desc_%d" % i])
+        assert _pose_close(od.c_T_w, g["cTw_%d" % i]), i
+    assert calls.count("point_clouds") == len(g["left"]) - 1 and "transform" in calls
+
+    class Blind(StereoOdometer):
+        def feature_mask(self, disparity):
+            return np.zeros(disparity.shape, np.uint8)
+
+    blind = Blind(cam, nfeatures=n, preprocessed_frames=True)
+    assert blind.update(g["left"][0], g["right"][0]) is False and blind.skip_cause == "keypoints"
+
+    # save_frame_update with the reference's signature + assignable state: seed an odometer with the products of frame 0 taken
+    # from another odometer, then continue with frame 1 on the fused path
+    src = StereoOdometer(cam, nfeatures=n, preprocessed_frames=True)
+    assert src.update(g["left"][0], g["right"][0])
+    dst = StereoOdometer(cam, nfeatures=n, preprocessed_frames=True)
+    assert dst.current_img is None
+    dst.save_frame_update(src.current_img, src.current_disparity, src.current_3d, src.current_kps, src.current_desc)
+    assert dst.prev_img is None and np.array_equal(dst.current_desc, src.current_desc) and len(dst.current_kps) == len(src.current_kps)
+    assert dst.update(g["left"][1], g["right"][1]) and src.update(g["left"][1], g["right"][1])
+    assert np.array_equal(dst.c_T_w, src.c_T_w)
+    dst.current_desc = dst.current_desc.copy()       # plain attribute semantics: assignable
+    dst.prev_kps = dst.prev_kps
+    assert dst.update(g["left"][2], g["right"][2]) and src.update(g["left"][2], g["right"][2])
+    assert np.array_equal(dst.c_T_w, src.c_T_w)
+    with pytest.raises(cv2.error):
+        src.update(g["left"][0][:, :-1], g["right"][0])
+    with pytest.raises(cv2.error):
+        cam.stereoSGBM.compute(g["left"][0].astype(np.float32), g["right"][0])
