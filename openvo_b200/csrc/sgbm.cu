@@ -272,9 +272,9 @@ __device__ __forceinline__ void path_step(PathState<NPR>& s, const uint32_t (&c)
     for (int r = 0; r < NPR; r++) {
         const uint32_t dm1 = r == 0 ? below : s.L[r - 1];        // Lp[d-1]
         const uint32_t dp1 = r == NPR - 1 ? above : s.L[r + 1];  // Lp[d+1]
-        uint32_t t = __viaddmin_u16x2(dm1, P1P1, s.L[r]);
-        t = __viaddmin_u16x2(dp1, P1P1, t);
-        t = __vminu2(t, mP2);
+        // min(Lp[d-1] + P1, Lp[d+1] + P1, Lp[d], m + P2): the two neighbours share their "+ P1" (a plain add: no half can carry,
+        // MAX_COST + P1 < 2^16), then one three-way minimum — two half-rate DPX instructions per word instead of three
+        const uint32_t t = __vimin3_u16x2(__vminu2(dm1, dp1) + P1P1, s.L[r], mP2);
         out[r] = c[r] + (t - s.mm);
         if (PAD) out[r] |= padmask[r];
     }
