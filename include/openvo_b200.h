@@ -100,6 +100,15 @@ int ovo_orb_detect_compute(ovo_ctx* ctx, const uint8_t* img_dev, const uint8_t* 
 int ovo_orb_detect_begin(ovo_ctx* ctx, const uint8_t* img_dev, const uint8_t* mask_dev, int nb, void* stream);
 int ovo_orb_detect_finish(ovo_ctx* ctx, int nb, float* kp_dev, uint8_t* desc_dev, int* n_kp_host, void* stream);
 
+/* Whole-frame entry — the per-frame part of StereoOdometer.update that does not depend on the previous frame
+ * (ref: src/openVO/stereo_odometer.py:116-117 = stereo.compute_3d + orb.detectAndCompute with feature_mask), in two halves like
+ * the ORB seam: `begin` queues ovo_sgbm_compute + ovo_disparity_post + ovo_crop_left + ovo_orb_detect_begin on `stream` and
+ * returns at once; `finish` == ovo_orb_detect_finish.  left/right: u8 [nb][height][pitch] rectified gray; disp16: i16
+ * [nb][height][width] scratch; disp_f32 / mask / img_crop: [nb][ch][cw] (kept by the caller as the frame's products). */
+int ovo_extract_begin(ovo_ctx* ctx, const uint8_t* left_dev, const uint8_t* right_dev, int pitch, size_t frame_stride, int nb,
+                      int16_t* disp16_dev, float* disp_f32_dev, uint8_t* mask_dev, uint8_t* img_crop_dev, void* stream);
+int ovo_extract_finish(ovo_ctx* ctx, int nb, float* kp_dev, uint8_t* desc_dev, int* n_kp_host, void* stream);
+
 /* Seam S-E — replaces matcher.knnMatch(desc1, desc2, k=2) (ref: src/openVO/stereo_odometer.py:163).
  * nn: i32 [nq][4] = (trainIdx0, dist0, trainIdx1, dist1); ties resolve to the lowest train index. */
 int ovo_knn2_hamming(ovo_ctx* ctx, const uint8_t* q_desc_dev, int nq, const uint8_t* t_desc_dev, int nt, int32_t* nn_dev,

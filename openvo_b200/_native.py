@@ -67,6 +67,8 @@ _SIGNATURES = {
     "ovo_orb_detect_compute": (_i, [_vp, _vp, _vp, _i, _vp, _vp, ctypes.POINTER(_i), _vp]),
     "ovo_orb_detect_begin": (_i, [_vp, _vp, _vp, _i, _vp]),
     "ovo_orb_detect_finish": (_i, [_vp, _i, _vp, _vp, ctypes.POINTER(_i), _vp]),
+    "ovo_extract_begin": (_i, [_vp, _vp, _vp, _i, _sz, _i, _vp, _vp, _vp, _vp, _vp]),
+    "ovo_extract_finish": (_i, [_vp, _i, _vp, _vp, ctypes.POINTER(_i), _vp]),
     "ovo_knn2_hamming": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),
     "ovo_match_points": (_i, [_vp, _vp, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ovo_rigid_transform": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),

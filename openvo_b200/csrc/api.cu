@@ -379,6 +379,18 @@ int ovo_orb_detect_finish(ovo_ctx* c, int nb, float* kp, uint8_t* desc, int* n_k
     return orb_phase2_launch(d, &c->orb0, L.frame_bytes, nb, max_sel, c->nsel_dev, kp, desc, st);
 }
 
+int ovo_extract_begin(ovo_ctx* c, const uint8_t* left, const uint8_t* right, int pitch, size_t frame_stride, int nb, int16_t* disp16,
+                      float* disp_f32, uint8_t* mask, uint8_t* img_crop, void* stream) {
+    if (ovo_sgbm_compute(c, left, right, pitch, frame_stride, nb, disp16, stream)) return 1;
+    if (ovo_disparity_post(c, disp16, nb, disp_f32, mask, stream)) return 1;
+    if (ovo_crop_left(c, left, pitch, frame_stride, nb, img_crop, stream)) return 1;
+    return ovo_orb_detect_begin(c, img_crop, mask, nb, stream);
+}
+
+int ovo_extract_finish(ovo_ctx* c, int nb, float* kp, uint8_t* desc, int* n_kp_host, void* stream) {
+    return ovo_orb_detect_finish(c, nb, kp, desc, n_kp_host, stream);
+}
+
 int ovo_knn2_hamming(ovo_ctx* c, const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* nn, void* stream) {
     CHECK_CTX(c, 1);
     if (nq > c->L.orb.kp_cap || nt > c->L.orb.kp_cap) { set_error("descriptor count exceeds keypoint capacity"); return 1; }

@@ -613,7 +613,9 @@ void orb_make_dims(int W, int H, int nfeatures, OrbDims* d) {
     }
     d->lv[ORB_NLEVELS - 1].nfeat = nfeatures - sum > 0 ? nfeatures - sum : 0;
     d->cand_cap = off / 4 + 1024;  // strict 3x3 NMS leaves at most one candidate per 2x2 block
-    d->kp_cap = nfeatures + nfeatures / 8 + 64;
+    // retainBest keeps every tie at its boundary, so a frame can yield more than nfeatures keypoints (cv2 returns them all):
+    // room for 25 % + 128 extra; beyond that ovo_orb_detect_finish reports an error instead of silently truncating
+    d->kp_cap = nfeatures + nfeatures / 4 + 128;
 }
 
 size_t orb_workspace_bytes(const OrbDims& d) {

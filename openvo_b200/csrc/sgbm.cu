@@ -1314,11 +1314,14 @@ int launch_paths(const SgbmDims& d, const SgbmWorkspace& ws, size_t ws_stride, i
 #ifndef OVO_VS_BR
 #define OVO_VS_BR 16
 #endif
+#ifndef OVO_VS_BR256
+#define OVO_VS_BR256 8
+#endif
         auto vs = [&](auto sat) -> int {
             constexpr bool SAT = decltype(sat)::value;
             if constexpr (NPR == 1) return launch_vsum<8, 4, PAD, OVO_VS_BR, OVO_VS_VG, SAT>(d, ws, ws_stride, nb, st);        // Dp = 64
             else if constexpr (NPR == 2) return launch_vsum<8, 8, PAD, OVO_VS_BR, OVO_VS_VG, SAT>(d, ws, ws_stride, nb, st);   // Dp = 128
-            else return launch_vsum<16, 8, PAD, 8, 16, SAT>(d, ws, ws_stride, nb, st);                                  // Dp = 256
+            else return launch_vsum<16, 8, PAD, OVO_VS_BR256, 16, SAT>(d, ws, ws_stride, nb, st);                       // Dp = 256
         };
         rc = nosat ? vs(std::false_type()) : vs(std::true_type());
         if (rc) return rc;

@@ -280,10 +280,13 @@ class Engine:
 
     def frames_begin(self, left, right):
         """Queue disparity + detection for a batch without waiting (one batch in flight per engine) -> token for frames_finish."""
-        disp16 = self.sgbm(left, right)
-        disp, mask = self.disparity_post(disp16)
-        img = self.crop(left)
-        self.orb_begin(img, mask)
+        nb = left.shape[0]
+        disp16 = torch.empty((nb, self.H, self.W), dtype=torch.int16, device=self.device)
+        disp = torch.empty((nb, self.ch, self.cw), dtype=torch.float32, device=self.device)
+        mask = torch.empty((nb, self.ch, self.cw), dtype=torch.uint8, device=self.device)
+        img = torch.empty((nb, self.ch, self.cw), dtype=torch.uint8, device=self.device)
+        N.check(self.lib, self.lib.ovo_extract_begin(self.ctx, left.data_ptr(), right.data_ptr(), self.W, self.W * self.H, nb,
+                                                     disp16.data_ptr(), disp.data_ptr(), mask.data_ptr(), img.data_ptr(), self._stream()))
         return (left, right, disp16, disp, mask, img)  # inputs and intermediates stay referenced while the device uses them
 
     def frames_finish(self, token):
