@@ -27,8 +27,8 @@ sys.path.insert(0, ROOT)
 
 CONFIGS = {
     "K": dict(W=1241, H=376, D=128, n=2000, seqs=48, name="KITTI-shaped 1241x376 stereo, ORB 2000 kp, StereoSGBM 128 disp"),
-    "F": dict(W=1920, H=1080, D=256, n=5000, seqs=16, name="1920x1080 stereo, ORB 5000 kp, StereoSGBM 256 disp"),
-    "U": dict(W=3840, H=2160, D=256, n=10000, seqs=4, name="3840x2160 stereo, ORB 10000 kp, StereoSGBM 256 disp"),
+    "F": dict(W=1920, H=1080, D=256, n=5000, seqs=32, name="1920x1080 stereo, ORB 5000 kp, StereoSGBM 256 disp"),
+    "U": dict(W=3840, H=2160, D=256, n=10000, seqs=8, name="3840x2160 stereo, ORB 10000 kp, StereoSGBM 256 disp"),
     "S": dict(W=640, H=200, D=64, n=500, seqs=48, name="small 640x200 stereo, ORB 500 kp, StereoSGBM 64 disp (dev only)"),
 }
 N_DISTINCT = 6  # distinct rendered frames; sequences ping-pong through them with different phases
@@ -176,13 +176,16 @@ def single_sequence(cam, cfg, pin_L, pin_R, L, R, n_frames=200):
     idx = [frame_index(s, 0) for s in range(n_frames)]
     lefts, rights = [pin_L[i] for i in idx], [pin_R[i] for i in idx]
     od = SequenceOdometer(cam, chunk=24, nfeatures=cfg["n"], preprocessed_frames=True)
-    od.run(lefts[:48], rights[:48])  # warm-up: allocations, first launches
-    od = SequenceOdometer(cam, chunk=24, nfeatures=cfg["n"], preprocessed_frames=True)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    oks = od.run(lefts, rights)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    od.run(lefts, rights)  # warm-up: the whole sequence once (allocator, pinned staging, first launches)
+    runs = []
+    for _ in range(3):
+        od = SequenceOdometer(cam, chunk=24, nfeatures=cfg["n"], preprocessed_frames=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        oks = od.run(lefts, rights)
+        torch.cuda.synchronize()
+        runs.append(n_frames / (time.perf_counter() - t0))
+    dt = n_frames / float(np.median(runs))
     st = StereoOdometer(cam, nfeatures=cfg["n"], preprocessed_frames=True, _engine_tag=998)
     for k in range(3):
         st.update(L[idx[k]], R[idx[k]])
@@ -193,7 +196,7 @@ def single_sequence(cam, cfg, pin_L, pin_R, L, R, n_frames=200):
     torch.cuda.synchronize()
     dts = time.perf_counter() - t0
     return {"workload": "one synthetic %s sequence of %d frames, host frames in, poses out" % (cfg["name"], n_frames),
-            "value": n_frames / dt, "unit": "frames/s", "chunk": 24, "frames_committed": int(sum(oks)),
+            "value": n_frames / dt, "unit": "frames/s", "runs": runs, "chunk": 24, "frames_committed": int(sum(oks)),
             "streaming_update_frames_per_s": n_frames / dts, "streaming_ms_per_frame": 1e3 * dts / n_frames,
             "identical_to_streaming": bool(oks == want and np.array_equal(od.c_T_w, st.c_T_w) and od.skip_cause == st.skip_cause)}
 
@@ -567,7 +570,11 @@ def main():
             pass
         roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": which, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": abytes,
-                    "ms_per_launch": dur_s * 1e3, "share_of_step": prof[top][0] / tot}
+                    "ms_per_launch": dur_s * 1e3, "share_of_step": prof[top][0] / tot,
+                    "note": "kernel with the largest share of the step.  Since round 2 the path kernels write ONE vertical volume "
+                            "(Sv) instead of three, which halves their algorithmic bytes; they are no longer HBM-bound (ncu: DRAM 29 % "
+                            "for k_sgbm_vsum, 55 % for k_sgbm_horiz) but bound by the ALU / DPX pipe (54 % / 72 % pipe utilisation, "
+                            "profiles/r02_ncu_full_summary.txt), so this HBM fraction is low by construction"}
     stages = None
     if rank == 0 and per_kernel:
         # per-stage view (SURVEY.md §8(d) contract numerators); times are per frame from the single-stream event profile

@@ -586,7 +586,7 @@ __global__ void __launch_bounds__(32 * vs_warps<LPC, BR, VG>(), vs_ctas_per_sm<L
     const size_t vol = (size_t)H * W1 * DH;  // words
     const uint32_t* __restrict__ C = reinterpret_cast<const uint32_t*>(frame_ptr(ws.C, ws_stride, f));
     uint32_t* Sv = reinterpret_cast<uint32_t*>(frame_ptr(ws.Lv, ws_stride, f));
-    uint32_t* bb = Sv + vol;  // band-state buffer [2 parity][3 kinds][W1][DH], in the space of the second volume
+    uint32_t* bb = Sv + vol;  // band-state buffer [2 parity][3 kinds][W1][DH], right behind Sv
     const uint32_t* bb_in = bb + (size_t)(parity ^ 1) * 3 * W1 * DH;
     uint32_t* bb_out = bb + (size_t)parity * 3 * W1 * DH;
     // strip of band row rn: cells [x0 - BR, x0 + B + BR) of image row y0 + rn (running over the row ends into the neighbouring
@@ -1285,6 +1285,8 @@ static bool use_fused_vertical() {
     return on;
 }
 
+static bool fused_vertical(const SgbmDims& d) { return d.mode == 0 && use_fused_vertical(); }
+
 template <int LPC, int NPR, bool PAD, int BR, int VG, bool SAT>
 int launch_vsum(const SgbmDims& d, const SgbmWorkspace& ws, size_t ws_stride, int nb, cudaStream_t st) {
     constexpr int B = vs_tile<LPC, VG>();
@@ -1301,8 +1303,7 @@ int launch_vsum(const SgbmDims& d, const SgbmWorkspace& ws, size_t ws_stride, in
 
 template <int NPR, bool PAD>
 int launch_paths(const SgbmDims& d, const SgbmWorkspace& ws, size_t ws_stride, int nb, cudaStream_t st) {
-    // the band-state buffer of the fused kernel lives in the second volume: 6 * W1 vectors must fit into two volumes
-    const bool fused = d.mode == 0 && d.H >= 4 && use_fused_vertical();
+    const bool fused = fused_vertical(d);
     // no sum of five path costs can reach MAX_COST: the sums need no saturation (SURVEY.md A.4 bounds C by bs^2 * (2 ftzero + 63))
     // (padded disparities then hold 5 * 0x7FFF mod 2^16 = 32763 after the sums, still above every real sum: keep a margin)
     const bool nosat = 5 * (d.bs * d.bs * (2 * d.ftzero + 63) + d.P2) <= 32000;
@@ -1369,10 +1370,18 @@ static size_t ckpt_bytes(const SgbmDims& d) {
     return align_up((size_t)d.H * 2 * sph * d.Dp * 2, 256);
 }
 
+// bytes of the vertical-path region that follows C: ONE volume (Sv) plus the band-state buffer [2][3][W1] vectors for the fused
+// kernel, three volumes (six in MODE_HH) for the one-volume-per-direction kernel
+static size_t lv_bytes(const SgbmDims& d) {
+    const size_t vol = align_up((size_t)d.H * d.W1 * d.Dp * 2, 256);
+    if (fused_vertical(d)) return align_up((size_t)d.H * d.W1 * d.Dp * 2 + (size_t)6 * d.W1 * d.Dp * 2, 256);
+    return (d.mode ? 6 : 3) * vol;
+}
+
 size_t sgbm_workspace_bytes(const SgbmDims& d) {
     const size_t vol = align_up((size_t)d.H * d.W1 * d.Dp * 2, 256);
     const size_t img = align_up((size_t)d.H * d.W * 4, 256);
-    return align_up(4 * img /*prep*/ + (d.mode ? 7 : 4) * vol /*C + Lv[3]*/ + ckpt_bytes(d) + 4 * img /*raw, med (i16) + label, csize (i32) -> 2*0.5+2 = 3 img*/, 256);
+    return align_up(4 * img /*prep*/ + vol /*C*/ + lv_bytes(d) + ckpt_bytes(d) + 4 * img /*raw, med (i16) + label, csize (i32) -> 2*0.5+2 = 3 img*/, 256);
 }
 
 void sgbm_carve(const SgbmDims& d, uint8_t* base, SgbmWorkspace* ws) {
@@ -1381,7 +1390,7 @@ void sgbm_carve(const SgbmDims& d, uint8_t* base, SgbmWorkspace* ws) {
     uint8_t* p = base;
     ws->prep = reinterpret_cast<uint32_t*>(p); p += 4 * img;
     ws->C = reinterpret_cast<int16_t*>(p); p += vol;
-    ws->Lv = reinterpret_cast<int16_t*>(p); p += (d.mode ? 6 : 3) * vol;
+    ws->Lv = reinterpret_cast<int16_t*>(p); p += lv_bytes(d);
     ws->ckpt = reinterpret_cast<int16_t*>(p); p += ckpt_bytes(d);
     ws->raw = reinterpret_cast<int16_t*>(p); p += img / 2;
     ws->med = reinterpret_cast<int16_t*>(p); p += img / 2;
