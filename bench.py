@@ -395,7 +395,8 @@ def main():
         cpu_baseline["stages_ms_per_frame"] = prof.get("stages_ms")
 
     if "OVO_SELECT_THREADS" not in os.environ:
-        os.environ["OVO_SELECT_THREADS"] = str(a.select_threads or max(2, min(8, host_cores() // max(1, world))))
+        # host threads for the per-frame retainBest ordering: the rank's share of the cores minus one for the driving thread
+        os.environ["OVO_SELECT_THREADS"] = str(a.select_threads or max(2, min(8, host_cores() // max(1, world) - 1)))
     import torch
     import torch.distributed as dist
     from openvo_b200 import StereoCamera, synth, _native

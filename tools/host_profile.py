@@ -11,7 +11,7 @@ from openvo_b200.batch import BatchOdometer
 cfg = bench.CONFIGS["K"]
 L, R = bench.make_frames(cfg)
 cam = StereoCamera(**synth.camera_args(cfg["W"], cfg["H"], cfg["D"]))
-SP = 8
+SP = 24
 bo = BatchOdometer(cam, SP, nfeatures=cfg["n"], engine_tag=0, preprocessed_frames=True)
 dev_L, dev_R = torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()
 
