@@ -90,7 +90,7 @@ struct OrbWorkspace {           // per frame, device pointers
     uint32_t* candmask;                      // [total_mwords] one bit per pixel: NMS + border + mask survivor
     int32_t* lvl_count;                      // [64]: [0..7] candidates per level, [8..15] level offsets, [16] total; survivors of the
                                              // first retainBest (FAST score >= the level's boundary score): [17..24] per level,
-                                             // [25..32] offsets, [33] total
+                                             // [25..32] offsets, [33] total, [34..41] the levels' boundary scores
     int32_t* cand_xy;                        // [cand_cap] packed (y<<16 | x)
     uint8_t* cand_score;                     // [cand_cap] FAST score
     float* cand_harris;                      // [cand_cap] Harris response (written for survivors only)

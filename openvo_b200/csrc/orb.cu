@@ -295,67 +295,73 @@ __device__ __forceinline__ int cand_level(const int32_t* lvl, int i) {
 // KeyPointsFilter::retainBest(2 * n_l) on the FAST score keeps every candidate whose score reaches the (2 n_l)-th largest one
 // (all ties at the boundary stay).  That SET needs no ordering: a 256-bin histogram of the 8-bit scores gives the boundary,
 // an ordered compaction the survivors' ids.  Only they get a Harris response, and only their responses travel to the host,
-// which still produces the survivors' ORDER (libstdc++'s introselect permutation, host_select.cpp).  One CTA per frame.
-__global__ void __launch_bounds__(1024) k_orb_survivors(OrbDims d, OrbWorkspace ws, size_t ws_stride) {
+// which still produces the survivors' ORDER (libstdc++'s introselect permutation, host_select.cpp).
+// Pass A (one CTA per frame and level): boundary score of the level and the number of survivors.
+__global__ void __launch_bounds__(1024) k_orb_survivors_count(OrbDims d, OrbWorkspace ws, size_t ws_stride) {
     __shared__ int hist[256];
+    __shared__ int s_amb;
+    const int f = blockIdx.y, l = blockIdx.x;
+    int32_t* lvl = fptr(ws.lvl_count, ws_stride, f);
+    const uint8_t* score = fptr(ws.cand_score, ws_stride, f);
+    const int base = lvl[ORB_NLEVELS + l], n = min(lvl[l], max(d.cand_cap - base, 0)), keep = 2 * d.lv[l].nfeat;
+    if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+    __syncthreads();
+    if (n > keep && keep > 0)
+        for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&hist[score[base + i]], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int amb = 0, cnt = n;             // n <= keep: nothing is cut
+        if (keep == 0) { amb = 256; cnt = 0; }  // retainBest(0): nothing survives
+        else if (n > keep) {
+            cnt = 0;
+            for (amb = 255; amb > 0; amb--) {
+                cnt += hist[amb];
+                if (cnt >= keep) break;
+            }
+            if (amb == 0) cnt += hist[0];
+        }
+        s_amb = amb;
+        lvl[17 + l] = cnt;
+        lvl[34 + l] = amb;
+    }
+}
+
+// Pass B (one CTA per frame and level): ordered compaction of the level's survivors behind those of the lower levels.
+__global__ void __launch_bounds__(1024) k_orb_survivors(OrbDims d, OrbWorkspace ws, size_t ws_stride) {
     __shared__ int warp_sums[32];
-    __shared__ int s_amb, s_base;
-    const int f = blockIdx.x;
+    const int f = blockIdx.y, l = blockIdx.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     int32_t* lvl = fptr(ws.lvl_count, ws_stride, f);
     const uint8_t* score = fptr(ws.cand_score, ws_stride, f);
     int32_t* surv = fptr(ws.surv_id, ws_stride, f);
-    if (threadIdx.x == 0) s_base = 0;
-    for (int l = 0; l < ORB_NLEVELS; l++) {
-        const int n = min(lvl[l], max(d.cand_cap - lvl[ORB_NLEVELS + l], 0)), base = lvl[ORB_NLEVELS + l], keep = 2 * d.lv[l].nfeat;
-        if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+    const int base = lvl[ORB_NLEVELS + l], n = min(lvl[l], max(d.cand_cap - base, 0)), amb = lvl[34 + l];
+    int out0 = 0;
+    for (int k = 0; k < l; k++) out0 += lvl[17 + k];
+    int done = 0;  // survivors of the chunks before this one
+    for (int i0 = 0; i0 < n; i0 += 1024) {
+        const int i = i0 + threadIdx.x;
+        const bool p = i < n && (int)score[base + i] >= amb;
+        const uint32_t bal = __ballot_sync(0xffffffffu, p);
+        if (lane == 0) warp_sums[wid] = __popc(bal);
         __syncthreads();
-        if (n > keep && keep > 0)
-            for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&hist[score[base + i]], 1);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int amb = 0;                      // n <= keep: nothing is cut
-            if (keep == 0) amb = 256;         // retainBest(0): nothing survives
-            else if (n > keep) {
-                int acc = 0;
-                for (amb = 255; amb > 0; amb--) {
-                    acc += hist[amb];
-                    if (acc >= keep) break;
-                }
-            }
-            s_amb = amb;
-        }
-        __syncthreads();
-        const int amb = s_amb, out0 = s_base;
-        int done = 0;  // survivors of the chunks before this one
-        for (int i0 = 0; i0 < n; i0 += 1024) {
-            const int i = i0 + threadIdx.x;
-            const bool p = i < n && (int)score[base + i] >= amb;
-            const uint32_t bal = __ballot_sync(0xffffffffu, p);
-            if (lane == 0) warp_sums[wid] = __popc(bal);
-            __syncthreads();
-            if (wid == 0) {
-                int s = warp_sums[lane];
+        if (wid == 0) {
+            int s = warp_sums[lane];
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int t = __shfl_up_sync(0xffffffffu, s, o);
-                    if (lane >= o) s += t;
-                }
-                warp_sums[lane] = s;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, s, o);
+                if (lane >= o) s += t;
             }
-            __syncthreads();
-            if (p) surv[out0 + done + (wid ? warp_sums[wid - 1] : 0) + __popc(bal & ((1u << lane) - 1))] = base + i;
-            done += warp_sums[31];
-            __syncthreads();
+            warp_sums[lane] = s;
         }
-        if (threadIdx.x == 0) {
-            lvl[17 + l] = done;
-            lvl[25 + l] = out0;
-            s_base = out0 + done;
-        }
+        __syncthreads();
+        if (p) surv[out0 + done + (wid ? warp_sums[wid - 1] : 0) + __popc(bal & ((1u << lane) - 1))] = base + i;
+        done += warp_sums[31];
         __syncthreads();
     }
-    if (threadIdx.x == 0) lvl[33] = s_base;
+    if (threadIdx.x == 0) {
+        lvl[25 + l] = out0;
+        if (l == ORB_NLEVELS - 1) lvl[33] = out0 + done;
+    }
 }
 
 // ---- Harris response of the survivors (A.1.6) ------------------------------------------------------------------------------
@@ -693,7 +699,9 @@ int orb_phase1_launch(const OrbDims& d, const OrbWorkspace* ws0, size_t ws_strid
         OVO_LAUNCH_CHECK();
     }
     {
-        OVO_LAUNCH(k_orb_survivors, dim3(nb), dim3(1024), 0, st, d, ws, ws_stride);
+        OVO_LAUNCH(k_orb_survivors_count, dim3(ORB_NLEVELS, nb), dim3(1024), 0, st, d, ws, ws_stride);
+        OVO_LAUNCH_CHECK();
+        OVO_LAUNCH(k_orb_survivors, dim3(ORB_NLEVELS, nb), dim3(1024), 0, st, d, ws, ws_stride);
         OVO_LAUNCH_CHECK();
         dim3 grid(cdiv(d.cand_cap, 128), nb);
         OVO_LAUNCH(k_orb_harris, grid, dim3(128), 0, st, d, ws, ws_stride);
