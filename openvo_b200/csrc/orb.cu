@@ -38,25 +38,34 @@ __device__ __forceinline__ T* fptr(T* p, size_t stride_bytes, int f) {
 // tab: per destination index (src index | c1 << 16), c1 = weight of src[index+1] in 1/256
 __global__ void __launch_bounds__(256) k_orb_resize(OrbDims d, OrbWorkspace ws, size_t ws_stride, int level,
                                                     const int32_t* __restrict__ xtab, const int32_t* __restrict__ ytab, int has_mask) {
+    // a thread produces 4 horizontally adjacent pixels of one row: one division and one row-table look-up per thread, and the
+    // source bytes of neighbouring outputs come from the same cache lines
     const OrbLevel L = d.lv[level], S = d.lv[level - 1];
-    const int f = blockIdx.y, n = L.w * L.h;
+    const int f = blockIdx.y, W4 = (L.w + 3) >> 2;
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= W4 * L.h) return;
+    const int y = t / W4, x0 = (t - y * W4) * 4;
+    const int ty = ytab[y];
+    const int j0 = ty & 0xFFFF, cy = ty >> 16, j1 = min(j0 + 1, S.h - 1);
+    int i0[4], i1[4], cx[4];
 #pragma unroll
-    for (int e = 0; e < 4; e++) {  // 4 pixels per thread: 1024 consecutive pixels per CTA
-        const int i = (blockIdx.x * 4 + e) * 256 + threadIdx.x;
-        if (i >= n) break;
-        const int y = i / L.w, x = i - y * L.w;
-        const int tx = xtab[x], ty = ytab[y];
-        const int i0 = tx & 0xFFFF, cx = tx >> 16, j0 = ty & 0xFFFF, cy = ty >> 16;
-        const int i1 = min(i0 + 1, S.w - 1), j1 = min(j0 + 1, S.h - 1);
-        for (int pl = 0; pl < 1 + has_mask; pl++) {
-            uint8_t* base = fptr(pl ? ws.maskpyr : ws.pyr, ws_stride, f);
-            const uint8_t* r0 = base + S.off + (size_t)j0 * S.w;
-            const uint8_t* r1 = base + S.off + (size_t)j1 * S.w;
-            const uint32_t h0 = r0[i0] * (256 - cx) + r0[i1] * cx;
-            const uint32_t h1 = r1[i0] * (256 - cx) + r1[i1] * cx;
+    for (int e = 0; e < 4; e++) {
+        const int tx = xtab[min(x0 + e, L.w - 1)];
+        i0[e] = tx & 0xFFFF; cx[e] = tx >> 16; i1[e] = min(i0[e] + 1, S.w - 1);
+    }
+    for (int pl = 0; pl < 1 + has_mask; pl++) {
+        uint8_t* base = fptr(pl ? ws.maskpyr : ws.pyr, ws_stride, f);
+        const uint8_t* r0 = base + S.off + (size_t)j0 * S.w;
+        const uint8_t* r1 = base + S.off + (size_t)j1 * S.w;
+        uint8_t* out = base + L.off + (size_t)y * L.w + x0;
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            if (x0 + e >= L.w) break;
+            const uint32_t h0 = r0[i0[e]] * (256 - cx[e]) + r0[i1[e]] * cx[e];
+            const uint32_t h1 = r1[i0[e]] * (256 - cx[e]) + r1[i1[e]] * cx[e];
             uint32_t v = (h0 * (256 - cy) + h1 * cy + (1u << 15)) >> 16;
             if (pl) v = v > 254 ? v : 0;  // THRESH_TOZERO(254) on the mask levels
-            base[L.off + i] = (uint8_t)v;
+            out[e] = (uint8_t)v;
         }
     }
 }
@@ -686,7 +695,7 @@ int orb_phase1_launch(const OrbDims& d, const OrbWorkspace* ws0, size_t ws_strid
         OVO_LAUNCH_CHECK();
     }
     for (int l = 1; l < ORB_NLEVELS; l++) {
-        dim3 grid(cdiv(d.lv[l].w * d.lv[l].h, 1024), nb);
+        dim3 grid(cdiv(((d.lv[l].w + 3) / 4) * d.lv[l].h, 256), nb);
         OVO_LAUNCH(k_orb_resize, grid, dim3(256), 0, st, d, ws, ws_stride, l, tab_dev + tab_off[2 * l], tab_dev + tab_off[2 * l + 1], has_mask);
         OVO_LAUNCH_CHECK();
     }

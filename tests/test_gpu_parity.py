@@ -486,3 +486,19 @@ def test_reference_method_surface(golden):
         src.update(g["left"][0][:, :-1], g["right"][0])
     with pytest.raises(cv2.error):
         cam.stereoSGBM.compute(g["left"][0].astype(np.float32), g["right"][0])
+
+
+def test_sgbm_one_volume_per_direction_path():
+    """OVO_SGBM_FUSED=0 (the switch is read once per process -> child interpreter): the unfused vertical kernel, the A/B partner of
+    k_sgbm_vsum and what MODE_HH builds on, stays bit-exact on the GPU too."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = ("import sys; sys.path[:0] = [%r, %r]; import numpy as np; from conftest import occluded_pair; "
+            "from openvo_b200 import StereoCamera, synth; from oracle import openvo_port as O\n"
+            "for W, H, D in ((320, 96, 64), (1241, 376, 128), (400, 100, 256)):\n"
+            "    a = synth.camera_args(W, H, D); L, R = occluded_pair(W, H, d=min(24, D // 2))\n"
+            "    assert np.array_equal(StereoCamera(**a).stereoSGBM.compute(L, R), O.sgbm_compute(L, R, a['sgbm_params'])), (W, H, D)\n"
+            % (ROOT, os.path.join(ROOT, "tests")))
+    subprocess.run([sys.executable, "-c", code], check=True, env=dict(os.environ, OVO_SGBM_FUSED="0"))
