@@ -4,7 +4,8 @@
     python bench.py --gpus N --steps K --warmup W            # our arm
     python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path on the host cores
 
-A "step" advances S independent KITTI-shaped synthetic stereo sequences by one frame each on every GPU (BatchOdometer:
+A "step" advances S = 72 independent KITTI-shaped synthetic stereo sequences by one frame each on every GPU (three BatchOdometers
+of 24 sequences in flight on three streams, driven by one host thread:
 SGBM 128 disp + ORB 2000 kp + Hamming 2-NN/ratio + fused 3-D lookup + Umeyama + the reference's skip state machine), so a
 step is S frames per GPU (weak scaling: S per GPU is fixed).  `value` is measured with the frames already resident in
 HBM; `e2e` is the same loop through the public host-buffer API (numpy frames in pinned memory -> H2D every step, poses
@@ -26,10 +27,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CONFIGS = {
-    "K": dict(W=1241, H=376, D=128, n=2000, seqs=48, name="KITTI-shaped 1241x376 stereo, ORB 2000 kp, StereoSGBM 128 disp"),
-    "F": dict(W=1920, H=1080, D=256, n=5000, seqs=32, name="1920x1080 stereo, ORB 5000 kp, StereoSGBM 256 disp"),
-    "U": dict(W=3840, H=2160, D=256, n=10000, seqs=8, name="3840x2160 stereo, ORB 10000 kp, StereoSGBM 256 disp"),
-    "S": dict(W=640, H=200, D=64, n=500, seqs=48, name="small 640x200 stereo, ORB 500 kp, StereoSGBM 64 disp (dev only)"),
+    "K": dict(W=1241, H=376, D=128, n=2000, seqs=72, name="KITTI-shaped 1241x376 stereo, ORB 2000 kp, StereoSGBM 128 disp"),
+    "F": dict(W=1920, H=1080, D=256, n=5000, seqs=36, name="1920x1080 stereo, ORB 5000 kp, StereoSGBM 256 disp"),
+    "U": dict(W=3840, H=2160, D=256, n=10000, seqs=9, name="3840x2160 stereo, ORB 10000 kp, StereoSGBM 256 disp"),
+    "S": dict(W=640, H=200, D=64, n=500, seqs=72, name="small 640x200 stereo, ORB 500 kp, StereoSGBM 64 disp (dev only)"),
 }
 N_DISTINCT = 6  # distinct rendered frames; sequences ping-pong through them with different phases
 
@@ -186,6 +187,7 @@ def single_sequence(cam, cfg, pin_L, pin_R, L, R, n_frames=200):
         torch.cuda.synchronize()
         runs.append(n_frames / (time.perf_counter() - t0))
     dt = n_frames / float(np.median(runs))
+    trace = getattr(od, "trace", None)
     st = StereoOdometer(cam, nfeatures=cfg["n"], preprocessed_frames=True, _engine_tag=998)
     for k in range(3):
         st.update(L[idx[k]], R[idx[k]])
@@ -197,6 +199,7 @@ def single_sequence(cam, cfg, pin_L, pin_R, L, R, n_frames=200):
     dts = time.perf_counter() - t0
     return {"workload": "one synthetic %s sequence of %d frames, host frames in, poses out" % (cfg["name"], n_frames),
             "value": n_frames / dt, "unit": "frames/s", "runs": runs, "chunk": 24, "frames_committed": int(sum(oks)),
+            **({"host_ms_per_chunk_last_run(begin, extract+select, pair, replay)": [[round(1e3 * v, 2) for v in row] for row in trace]} if trace else {}),
             "streaming_update_frames_per_s": n_frames / dts, "streaming_ms_per_frame": 1e3 * dts / n_frames,
             "identical_to_streaming": bool(oks == want and np.array_equal(od.c_T_w, st.c_T_w) and od.skip_cause == st.skip_cause)}
 
@@ -331,11 +334,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="K", choices=list(CONFIGS))
     ap.add_argument("--seqs", type=int, default=0, help="independent sequences (= frames per step) per GPU; 0 = the config's default "
-                                                        "(48 at the KITTI shape: two batches of 24 in flight)")
+                                                        "(72 at the KITTI shape: three batches of 24 in flight)")
     ap.add_argument("--select-threads", type=int, default=0,
                     help="host threads per batch for the keypoint-selection step (OVO_SELECT_THREADS); 0 = min(8, cores / ranks)")
     ap.add_argument("--threads", type=int, default=1, help="host threads (each drives --groups batches round-robin)")
-    ap.add_argument("--groups", type=int, default=2,
+    ap.add_argument("--groups", type=int, default=3,
                     help="batches in flight per host thread: each has its own CUDA stream / workspace and a share of the sequences; the "
                          "thread finishes batch g of step s, queues batch g of step s+1 and moves on to g+1, so the host-side "
                          "keypoint selection of one batch overlaps device work of the others")

@@ -8,8 +8,8 @@ Extraction and disparity are independent per stereo pair; only the pose chain is
   3. replays the reference's skip / fall-back state machine (B4) serially on the host: a speculative result is used only if its
      first frame is in fact the odometer's current frame; after a failed frame the next one must be aligned to the last
      COMMITTED frame (and, on failure, to the one before it), so that pair is re-matched on demand — rare.
-Two chunks are in flight on two streams / workspaces so that the host-side keypoint selection of one overlaps device work of the
-other.  Results are identical to calling ``update`` frame by frame (same kernels, same state machine object).
+Three chunks are in flight on three streams / workspaces so that the host-side keypoint selection and state-machine replay of
+one overlap device work of the others.  Results are identical to calling ``update`` frame by frame (same kernels, same state machine object).
 """
 import numpy as np
 
@@ -17,9 +17,10 @@ from .stereo_odometer import StereoOdometer
 
 
 class SequenceOdometer(StereoOdometer):
-    def __init__(self, stereo_camera, chunk=24, **kw):
+    def __init__(self, stereo_camera, chunk=24, in_flight=3, **kw):
         super().__init__(stereo_camera, _max_batch=int(chunk), **kw)
         self.chunk = int(chunk)
+        self.in_flight = max(1, int(in_flight))  # chunks queued on the device at any time (one engine + stream each)
         self._active = None     # engine whose pair buffers hold the result being replayed
         self._streams = None
 
@@ -40,31 +41,40 @@ class SequenceOdometer(StereoOdometer):
         n = len(lefts)
         if n == 0:
             return []
-        engines = [self._chunk_engine(0), self._chunk_engine(1)]
+        NF = self.in_flight
+        engines = [self._chunk_engine(k) for k in range(NF)]
         if self._streams is None:
-            self._streams = [torch.cuda.Stream(device=engines[0].device) for _ in range(2)]
+            self._streams = [torch.cuda.Stream(device=engines[0].device) for _ in range(NF)]
         streams = self._streams
         bounds = [(i, min(i + self.chunk, n)) for i in range(0, n, self.chunk)]
-        tokens = [None, None]
+        tokens = [None] * NF
 
         def begin(c):
             i0, i1 = bounds[c]
-            eng = engines[c & 1]
-            with torch.cuda.stream(streams[c & 1]):
-                l, r = self.stereo._prepare_device(eng, lefts[i0:i1], rights[i0:i1], self.preprocessed_frames, key="seq%d" % (c & 1))
-                tokens[c & 1] = eng.frames_begin(l, r)
+            eng = engines[c % NF]
+            with torch.cuda.stream(streams[c % NF]):
+                l, r = self.stereo._prepare_device(eng, lefts[i0:i1], rights[i0:i1], self.preprocessed_frames, key="seq%d" % (c % NF))
+                tokens[c % NF] = eng.frames_begin(l, r)
 
+        import os
+        import time
+        trace = [] if os.environ.get("OVO_SEQ_TRACE") else None   # per-chunk host timings (begin, extract wait + select, pair, replay)
+        self.trace = trace
         out = []
         last = None  # the frame before the chunk's first one (committed or not: the speculation is checked at replay time)
-        begin(0)
+        for c in range(min(NF - 1, len(bounds))):
+            begin(c)
         try:
             for c in range(len(bounds)):
-                if c + 1 < len(bounds):
-                    begin(c + 1)
-                eng = engines[c & 1]
-                with torch.cuda.stream(streams[c & 1]):
-                    frames = eng.frames_finish(tokens[c & 1])
-                    tokens[c & 1] = None
+                t0 = time.perf_counter()
+                if c + NF - 1 < len(bounds):
+                    begin(c + NF - 1)
+                t1 = time.perf_counter()
+                eng = engines[c % NF]
+                with torch.cuda.stream(streams[c % NF]):
+                    frames = eng.frames_finish(tokens[c % NF])
+                    t2 = time.perf_counter()
+                    tokens[c % NF] = None
                     firsts = [last] + frames[:-1]
                     jobs, queued = [], {}
                     for k, (a, b) in enumerate(zip(firsts, frames)):
@@ -73,11 +83,14 @@ class SequenceOdometer(StereoOdometer):
                             queued[k] = a
                     eng.pair_batch_async(jobs, self.match_threshold, self.cross_check)
                     res = eng.pair_collect(len(frames)) if jobs else []
+                    t3 = time.perf_counter()
                     self._active = eng
                     for k, fr in enumerate(frames):
                         spec = (k, res[k]) if (k in queued and queued[k] is self._cur) else None
                         out.append(self._advance(fr, first=spec))
                     last = frames[-1]
+                    if trace is not None:
+                        trace.append((t1 - t0, t2 - t1, t3 - t2, time.perf_counter() - t3))
         finally:
             self._active = None
         return out
