@@ -104,7 +104,9 @@ int ovo_orb_detect_finish(ovo_ctx* ctx, int nb, float* kp_dev, uint8_t* desc_dev
  * (ref: src/openVO/stereo_odometer.py:116-117 = stereo.compute_3d + orb.detectAndCompute with feature_mask), in two halves like
  * the ORB seam: `begin` queues ovo_sgbm_compute + ovo_disparity_post + ovo_crop_left + ovo_orb_detect_begin on `stream` and
  * returns at once; `finish` == ovo_orb_detect_finish.  left/right: u8 [nb][height][pitch] rectified gray; disp16: i16
- * [nb][height][width] scratch; disp_f32 / mask / img_crop: [nb][ch][cw] (kept by the caller as the frame's products). */
+ * [nb][height][width] scratch; disp_f32 / mask / img_crop: [nb][ch][cw].  On a non-default stream the ~70 launches of `begin` are
+ * recorded once per distinct argument set into a CUDA graph and replayed as one launch afterwards (OVO_GRAPH=0 disables this), so
+ * callers should pass persistent buffers and copy the products they keep. */
 int ovo_extract_begin(ovo_ctx* ctx, const uint8_t* left_dev, const uint8_t* right_dev, int pitch, size_t frame_stride, int nb,
                       int16_t* disp16_dev, float* disp_f32_dev, uint8_t* mask_dev, uint8_t* img_crop_dev, void* stream);
 int ovo_extract_finish(ovo_ctx* ctx, int nb, float* kp_dev, uint8_t* desc_dev, int* n_kp_host, void* stream);

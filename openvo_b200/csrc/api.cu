@@ -151,6 +151,18 @@ struct ovo_ctx {
     int32_t* h_sel;    // [max_batch][kp_cap]
     int32_t* h_nsel;   // [max_batch]
     long long h2d_bytes = 0, d2h_bytes = 0;  // staging traffic of the keypoint selection
+#ifndef OVO_EMU
+    // CUDA graphs of ovo_extract_begin, one per distinct argument set (the Python engine calls it with persistent buffers, so
+    // there is one per batch size): ~70 kernel launches become one graph launch
+    struct ExtractGraph {
+        const void *left, *right, *disp16, *disp_f32, *mask, *img;
+        int pitch, nb;
+        size_t frame_stride;
+        cudaGraphExec_t exec;
+        long long launches;
+    };
+    std::vector<ExtractGraph> graphs;
+#endif
 };
 
 extern "C" {
@@ -265,6 +277,9 @@ ovo_ctx* ovo_create(const ovo_config* cfg, void* workspace_dev, size_t workspace
 
 void ovo_destroy(ovo_ctx* c) {
     if (!c) return;
+#ifndef OVO_EMU
+    for (auto& g : c->graphs) cudaGraphExecDestroy(g.exec);
+#endif
     if (c->h_lvl) cudaFreeHost(c->h_lvl);
     if (c->h_resp) cudaFreeHost(c->h_resp);
     if (c->h_sel) cudaFreeHost(c->h_sel);
@@ -379,12 +394,49 @@ int ovo_orb_detect_finish(ovo_ctx* c, int nb, float* kp, uint8_t* desc, int* n_k
     return orb_phase2_launch(d, &c->orb0, L.frame_bytes, nb, max_sel, c->nsel_dev, kp, desc, st);
 }
 
-int ovo_extract_begin(ovo_ctx* c, const uint8_t* left, const uint8_t* right, int pitch, size_t frame_stride, int nb, int16_t* disp16,
-                      float* disp_f32, uint8_t* mask, uint8_t* img_crop, void* stream) {
+static int extract_begin_launches(ovo_ctx* c, const uint8_t* left, const uint8_t* right, int pitch, size_t frame_stride, int nb,
+                                  int16_t* disp16, float* disp_f32, uint8_t* mask, uint8_t* img_crop, void* stream) {
     if (ovo_sgbm_compute(c, left, right, pitch, frame_stride, nb, disp16, stream)) return 1;
     if (ovo_disparity_post(c, disp16, nb, disp_f32, mask, stream)) return 1;
     if (ovo_crop_left(c, left, pitch, frame_stride, nb, img_crop, stream)) return 1;
     return ovo_orb_detect_begin(c, img_crop, mask, nb, stream);
+}
+
+int ovo_extract_begin(ovo_ctx* c, const uint8_t* left, const uint8_t* right, int pitch, size_t frame_stride, int nb, int16_t* disp16,
+                      float* disp_f32, uint8_t* mask, uint8_t* img_crop, void* stream) {
+    CHECK_CTX(c, nb);
+#ifndef OVO_EMU
+    static const bool use_graph = [] { const char* e = getenv("OVO_GRAPH"); return !(e && e[0] == '0'); }();
+    if (use_graph && !g_prof_on && stream != nullptr) {
+        cudaStream_t st = (cudaStream_t)stream;
+        for (auto& g : c->graphs)
+            if (g.left == left && g.right == right && g.disp16 == disp16 && g.disp_f32 == disp_f32 && g.mask == mask && g.img == img_crop &&
+                g.pitch == pitch && g.nb == nb && g.frame_stride == frame_stride) {
+                OVO_CUDA(cudaGraphLaunch(g.exec, st));
+                g_launches.fetch_add(g.launches, std::memory_order_relaxed);
+                return 0;
+            }
+        if (c->graphs.size() < 16) {
+            // first call with this argument set: record the launches into a graph (thread-local capture: other host threads
+            // driving other contexts are not affected), then replay it
+            const long long before = g_launches.load();
+            OVO_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            const int rc = extract_begin_launches(c, left, right, pitch, frame_stride, nb, disp16, disp_f32, mask, img_crop, stream);
+            cudaGraph_t graph = nullptr;
+            const cudaError_t e = cudaStreamEndCapture(st, &graph);
+            if (rc) { if (graph) cudaGraphDestroy(graph); return 1; }
+            if (e != cudaSuccess || !graph) { set_error("ovo_extract_begin: stream capture failed (%s)", cudaGetErrorString(e)); return 1; }
+            ovo_ctx::ExtractGraph g{left, right, disp16, disp_f32, mask, img_crop, pitch, nb, frame_stride, nullptr, g_launches.load() - before};
+            const cudaError_t ei = cudaGraphInstantiate(&g.exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ei != cudaSuccess) { set_error("ovo_extract_begin: graph instantiation failed (%s)", cudaGetErrorString(ei)); return 1; }
+            c->graphs.push_back(g);
+            OVO_CUDA(cudaGraphLaunch(g.exec, st));
+            return 0;
+        }
+    }
+#endif
+    return extract_begin_launches(c, left, right, pitch, frame_stride, nb, disp16, disp_f32, mask, img_crop, stream);
 }
 
 int ovo_extract_finish(ovo_ctx* c, int nb, float* kp, uint8_t* desc, int* n_kp_host, void* stream) {

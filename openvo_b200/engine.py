@@ -281,13 +281,25 @@ class Engine:
     def frames_begin(self, left, right):
         """Queue disparity + detection for a batch without waiting (one batch in flight per engine) -> token for frames_finish."""
         nb = left.shape[0]
-        disp16 = torch.empty((nb, self.H, self.W), dtype=torch.int16, device=self.device)
-        disp = torch.empty((nb, self.ch, self.cw), dtype=torch.float32, device=self.device)
-        mask = torch.empty((nb, self.ch, self.cw), dtype=torch.uint8, device=self.device)
-        img = torch.empty((nb, self.ch, self.cw), dtype=torch.uint8, device=self.device)
-        N.check(self.lib, self.lib.ovo_extract_begin(self.ctx, left.data_ptr(), right.data_ptr(), self.W, self.W * self.H, nb,
-                                                     disp16.data_ptr(), disp.data_ptr(), mask.data_ptr(), img.data_ptr(), self._stream()))
-        return (left, right, disp16, disp, mask, img)  # inputs and intermediates stay referenced while the device uses them
+        # persistent input / output buffers: ovo_extract_begin replays one CUDA graph per (buffers, batch size); the products a
+        # frame keeps (disparity, cropped image) are copied out of them
+        px = self.__dict__.get("_xbuf")
+        if px is None:
+            mb = self.max_batch
+            px = self._xbuf = dict(
+                left=torch.empty((mb, self.H, self.W), dtype=torch.uint8, device=self.device),
+                right=torch.empty((mb, self.H, self.W), dtype=torch.uint8, device=self.device),
+                disp16=torch.empty((mb, self.H, self.W), dtype=torch.int16, device=self.device),
+                disp=torch.empty((mb, self.ch, self.cw), dtype=torch.float32, device=self.device),
+                mask=torch.empty((mb, self.ch, self.cw), dtype=torch.uint8, device=self.device),
+                img=torch.empty((mb, self.ch, self.cw), dtype=torch.uint8, device=self.device))
+        px["left"][:nb].copy_(left, non_blocking=True)
+        px["right"][:nb].copy_(right, non_blocking=True)
+        N.check(self.lib, self.lib.ovo_extract_begin(self.ctx, px["left"].data_ptr(), px["right"].data_ptr(), self.W, self.W * self.H, nb,
+                                                     px["disp16"].data_ptr(), px["disp"].data_ptr(), px["mask"].data_ptr(),
+                                                     px["img"].data_ptr(), self._stream()))
+        disp, img = px["disp"][:nb].clone(), px["img"][:nb].clone()
+        return (left, right, None, disp, None, img)
 
     def frames_finish(self, token):
         _, _, _, disp, _, img = token
