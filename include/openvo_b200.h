@@ -99,6 +99,11 @@ int ovo_orb_detect_compute(ovo_ctx* ctx, const uint8_t* img_dev, const uint8_t* 
  * descriptor phase.  begin + finish on the same ctx / stream == ovo_orb_detect_compute. */
 int ovo_orb_detect_begin(ovo_ctx* ctx, const uint8_t* img_dev, const uint8_t* mask_dev, int nb, void* stream);
 int ovo_orb_detect_finish(ovo_ctx* ctx, int nb, float* kp_dev, uint8_t* desc_dev, int* n_kp_host, void* stream);
+/* `finish` on a worker thread of the library: returns at once; the worker waits for the detection phase on `stream`, runs the
+ * host-side retainBest the moment it lands and queues the descriptor phase, while the calling thread drives other contexts.
+ * ovo_orb_detect_wait joins it and reports its status; the caller must not use `stream` (nor n_kp_host) in between. */
+int ovo_orb_detect_finish_async(ovo_ctx* ctx, int nb, float* kp_dev, uint8_t* desc_dev, int* n_kp_host, void* stream);
+int ovo_orb_detect_wait(ovo_ctx* ctx);
 
 /* Whole-frame entry — the per-frame part of StereoOdometer.update that does not depend on the previous frame
  * (ref: src/openVO/stereo_odometer.py:116-117 = stereo.compute_3d + orb.detectAndCompute with feature_mask), in two halves like

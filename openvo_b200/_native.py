@@ -67,6 +67,8 @@ _SIGNATURES = {
     "ovo_orb_detect_compute": (_i, [_vp, _vp, _vp, _i, _vp, _vp, ctypes.POINTER(_i), _vp]),
     "ovo_orb_detect_begin": (_i, [_vp, _vp, _vp, _i, _vp]),
     "ovo_orb_detect_finish": (_i, [_vp, _i, _vp, _vp, ctypes.POINTER(_i), _vp]),
+    "ovo_orb_detect_finish_async": (_i, [_vp, _i, _vp, _vp, ctypes.POINTER(_i), _vp]),
+    "ovo_orb_detect_wait": (_i, [_vp]),
     "ovo_extract_begin": (_i, [_vp, _vp, _vp, _i, _sz, _i, _vp, _vp, _vp, _vp, _vp]),
     "ovo_extract_finish": (_i, [_vp, _i, _vp, _vp, ctypes.POINTER(_i), _vp]),
     "ovo_knn2_hamming": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),

@@ -2,7 +2,9 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <string>
@@ -151,6 +153,15 @@ struct ovo_ctx {
     int32_t* h_sel;    // [max_batch][kp_cap]
     int32_t* h_nsel;   // [max_batch]
     long long h2d_bytes = 0, d2h_bytes = 0;  // staging traffic of the keypoint selection
+    // ovo_orb_detect_finish_async: the second half of the ORB seam on a worker thread of the library
+    int device = 0;
+    std::thread worker;              // persistent (one CUDA per-thread initialisation, not one per batch): created on first use
+    std::mutex wmu;
+    std::condition_variable wcv;
+    std::function<int()> wjob;       // pending job
+    bool wbusy = false, wquit = false;
+    int worker_rc = 0;
+    char worker_err[512] = "";
 #ifndef OVO_EMU
     // CUDA graphs of ovo_extract_begin, one per distinct argument set (the Python engine calls it with persistent buffers, so
     // there is one per batch size): ~70 kernel launches become one graph launch
@@ -248,6 +259,7 @@ ovo_ctx* ovo_create(const ovo_config* cfg, void* workspace_dev, size_t workspace
         return nullptr;
     }
     ovo_ctx* c = new ovo_ctx();
+    cudaGetDevice(&c->device);
     c->h_lvl = nullptr; c->h_resp = nullptr; c->h_sel = nullptr; c->h_nsel = nullptr;
     c->cfg = *cfg; c->L = L; c->base = (uint8_t*)workspace_dev;
     sgbm_carve(L.sg, c->base, &c->sg0);
@@ -277,6 +289,15 @@ ovo_ctx* ovo_create(const ovo_config* cfg, void* workspace_dev, size_t workspace
 
 void ovo_destroy(ovo_ctx* c) {
     if (!c) return;
+    if (c->worker.joinable()) {
+        {
+            std::unique_lock<std::mutex> lk(c->wmu);
+            c->wcv.wait(lk, [&] { return !c->wbusy; });
+            c->wquit = true;
+        }
+        c->wcv.notify_all();
+        c->worker.join();
+    }
 #ifndef OVO_EMU
     for (auto& g : c->graphs) cudaGraphExecDestroy(g.exec);
 #endif
@@ -441,6 +462,54 @@ int ovo_extract_begin(ovo_ctx* c, const uint8_t* left, const uint8_t* right, int
 
 int ovo_extract_finish(ovo_ctx* c, int nb, float* kp, uint8_t* desc, int* n_kp_host, void* stream) {
     return ovo_orb_detect_finish(c, nb, kp, desc, n_kp_host, stream);
+}
+
+int ovo_orb_detect_finish_async(ovo_ctx* c, int nb, float* kp, uint8_t* desc, int* n_kp_host, void* stream) {
+    CHECK_CTX(c, nb);
+#ifdef OVO_EMU
+    c->worker_rc = ovo_orb_detect_finish(c, nb, kp, desc, n_kp_host, stream);
+    if (c->worker_rc) snprintf(c->worker_err, sizeof(c->worker_err), "%s", ovo_last_error());
+#else
+    std::unique_lock<std::mutex> lk(c->wmu);
+    if (c->wbusy) { set_error("ovo_orb_detect_finish_async: the previous call has not been waited for"); return 1; }
+    if (!c->worker.joinable()) {
+        c->worker = std::thread([c] {
+            cudaSetDevice(c->device);  // a new host thread starts on device 0
+            std::unique_lock<std::mutex> wl(c->wmu);
+            for (;;) {
+                c->wcv.wait(wl, [&] { return c->wquit || (c->wbusy && c->wjob); });
+                if (c->wquit) return;
+                std::function<int()> job = std::move(c->wjob);
+                c->wjob = nullptr;
+                wl.unlock();
+                const int rc = job();
+                wl.lock();
+                c->worker_rc = rc;
+                if (rc) snprintf(c->worker_err, sizeof(c->worker_err), "%s", ovo_last_error());  // the error string is thread-local
+                c->wbusy = false;
+                c->wcv.notify_all();
+            }
+        });
+    }
+    c->worker_rc = 0;
+    c->wjob = [=] { return ovo_orb_detect_finish(c, nb, kp, desc, n_kp_host, stream); };
+    c->wbusy = true;
+    lk.unlock();
+    c->wcv.notify_all();
+#endif
+    return 0;
+}
+
+int ovo_orb_detect_wait(ovo_ctx* c) {
+    if (!c) { set_error("null context"); return 1; }
+#ifndef OVO_EMU
+    {
+        std::unique_lock<std::mutex> lk(c->wmu);
+        c->wcv.wait(lk, [&] { return !c->wbusy; });
+    }
+#endif
+    if (c->worker_rc) { set_error("%s", c->worker_err); return 1; }
+    return 0;
 }
 
 int ovo_knn2_hamming(ovo_ctx* c, const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* nn, void* stream) {

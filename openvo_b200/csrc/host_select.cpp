@@ -43,26 +43,42 @@ void retain_best(std::vector<Rec>& k, int n) {
 // of the survivors is produced here.  out_sel receives candidate ids in final keypoint order.
 int orb_host_select(const OrbDims& d, const int32_t* lvl_count, const uint8_t* scores, const float* harris_dense, int32_t* out_sel) {
     int n_out = 0;
-    std::vector<Rec> k;
-    std::vector<int32_t> dense;
+    // scratch kept per host thread: no allocation per frame
+    static thread_local std::vector<uint32_t> a;   // first pass: (FAST score << 24 | index inside the level) — 4-byte records, integer compares
+    static thread_local std::vector<Rec> k;        // second pass: (Harris response, candidate id) of the survivors
+    static thread_local std::vector<int32_t> dense;
+    // the comparators look at the score only, exactly like the reference's `a.response > b.response` on KeyPoint records: the same
+    // comparison outcomes give the same introselect permutation
+    auto greater = [](uint32_t x, uint32_t y) { return (x >> 24) > (y >> 24); };
     for (int l = 0; l < ORB_NLEVELS; l++) {
-        const int n = lvl_count[l], base = lvl_count[ORB_NLEVELS + l];
-        k.resize(n);
-        for (int i = 0; i < n; i++) k[i] = {(float)scores[base + i], base + i};
-        retain_best(k, 2 * d.lv[l].nfeat);
-        // survivors = every candidate with score >= the boundary score (retainBest keeps all ties); the device numbered them in
-        // candidate order
-        float amb = 0.f;
-        if ((int)k.size() < n) {
-            amb = 256.f;
-            for (auto& r : k) amb = std::min(amb, r.resp);
+        const int n = lvl_count[l], base = lvl_count[ORB_NLEVELS + l], keep = 2 * d.lv[l].nfeat;
+        a.resize(n);
+        for (int i = 0; i < n; i++) a[i] = ((uint32_t)scores[base + i] << 24) | (uint32_t)i;
+        uint32_t amb = 0;  // boundary score: every candidate with score >= amb survives (retainBest keeps all ties)
+        if (n > keep) {
+            if (keep == 0) {
+                a.clear();
+                amb = 256;
+            } else {
+                std::nth_element(a.begin(), a.begin() + keep - 1, a.end(), greater);
+                amb = a[keep - 1] >> 24;
+                auto e = std::partition(a.begin() + keep, a.end(), [amb](uint32_t r) { return (r >> 24) >= amb; });
+                a.resize(e - a.begin());
+            }
         }
-        dense.assign(n, -1);
+        // the device numbered the survivors in candidate order
+        dense.resize(n);
         int j = lvl_count[25 + l];
-        for (int i = 0; i < n; i++)
-            if ((float)scores[base + i] >= amb) dense[i] = j++;
-        if (j - lvl_count[25 + l] != lvl_count[17 + l] || lvl_count[17 + l] != (int)k.size()) return -2;
-        for (auto& r : k) r.resp = harris_dense[dense[r.id - base]];
+        for (int i = 0; i < n; i++) {  // branch-free: the entry of a non-survivor is never read
+            dense[i] = j;
+            j += (uint32_t)scores[base + i] >= amb ? 1 : 0;
+        }
+        if (j - lvl_count[25 + l] != lvl_count[17 + l] || lvl_count[17 + l] != (int)a.size()) return -2;
+        k.resize(a.size());
+        for (size_t t = 0; t < a.size(); t++) {
+            const int i = (int)(a[t] & 0xFFFFFFu);
+            k[t] = {harris_dense[dense[i]], base + i};
+        }
         retain_best(k, d.lv[l].nfeat);
         if (n_out + (int)k.size() > d.kp_cap) return -1;
         for (auto& r : k) out_sel[n_out++] = r.id;

@@ -3,11 +3,18 @@
 PyTorch is used for device memory and streams only; every arithmetic step is a kernel behind include/openvo_b200.h.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
 
 from . import _native as N
+
+# Engine.async_finish: the host half of the ORB seam runs on a worker thread of the library (it starts the moment the detection
+# phase lands) instead of on the calling thread inside frames_finish.  It makes a single driver thread less sensitive to its own
+# latency (SequenceOdometer turns it on: 2400 -> 2950 frames/s) but costs host threads: with 8 ranks on 32 cores the batched
+# throughput drops (0.93 -> 0.85 of linear), so it is off by default.  OVO_ASYNC_FINISH=0/1 forces it for every engine.
+ASYNC_FINISH = {"0": False, "1": True}.get(os.environ.get("OVO_ASYNC_FINISH", ""), None)
 
 
 class Frame:
@@ -48,6 +55,7 @@ class Engine:
         if not self.ctx:
             raise N.NativeError(self.lib.ovo_last_error().decode())
         self._pin = {}
+        self.async_finish = False
         # persistent buffers of the pair step, one slot per frame of the batch
         nb = self.max_batch
         self.nn = torch.empty((nb, self.kp_cap, 4), dtype=torch.int32, device=self.device)
@@ -299,9 +307,21 @@ class Engine:
                                                      px["disp16"].data_ptr(), px["disp"].data_ptr(), px["mask"].data_ptr(),
                                                      px["img"].data_ptr(), self._stream()))
         disp, img = px["disp"][:nb].clone(), px["img"][:nb].clone()
-        return (left, right, None, disp, None, img)
+        # the second half of the ORB seam starts on a worker thread of the library the moment the detection phase lands
+        # (host-side retainBest, then the descriptor launch); frames_finish only joins it
+        kp = torch.empty((nb, self.kp_cap, N.KP_FIELDS), dtype=torch.float32, device=self.device)
+        desc = torch.empty((nb, self.kp_cap, 32), dtype=torch.uint8, device=self.device)
+        n = (ctypes.c_int * nb)()
+        started = self.async_finish if ASYNC_FINISH is None else ASYNC_FINISH
+        if started:
+            N.check(self.lib, self.lib.ovo_orb_detect_finish_async(self.ctx, nb, kp.data_ptr(), desc.data_ptr(), n, self._stream()))
+        return (left, right, kp, disp, desc, img, n, started)
 
     def frames_finish(self, token):
-        _, _, _, disp, _, img = token
-        kp, desc, n = self.orb_finish(img.shape[0])
+        _, _, kp, disp, desc, img, n, started = token
+        if started:
+            N.check(self.lib, self.lib.ovo_orb_detect_wait(self.ctx))
+        else:
+            N.check(self.lib, self.lib.ovo_orb_detect_finish(self.ctx, img.shape[0], kp.data_ptr(), desc.data_ptr(), n, self._stream()))
+        n = list(n)
         return [Frame(img[i], disp[i], kp[i], desc[i], n[i]) for i in range(img.shape[0])]

@@ -43,6 +43,8 @@ class SequenceOdometer(StereoOdometer):
             return []
         NF = self.in_flight
         engines = [self._chunk_engine(k) for k in range(NF)]
+        for e in engines:
+            e.async_finish = True   # one driver thread: let the library's worker start each chunk's host half as soon as it can
         if self._streams is None:
             self._streams = [torch.cuda.Stream(device=engines[0].device) for _ in range(NF)]
         streams = self._streams

@@ -47,6 +47,7 @@ static inline cudaError_t cudaFreeHost(void* p) { free(p); return 0; }
 static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = malloc(n); return 0; }
 static inline cudaError_t cudaFree(void* p) { free(p); return 0; }
 static inline cudaError_t cudaSetDevice(int) { return 0; }
+static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return 0; }
 template <typename T> static inline cudaError_t cudaFuncSetAttribute(T, int, int) { return 0; }
 enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 
