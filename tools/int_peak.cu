@@ -18,7 +18,9 @@ __global__ void __launch_bounds__(256) k(unsigned* out, unsigned seed) {
             if (OP == 0) v[i] = (v[i] + a) ^ b;                        // IADD3 / LOP3 (2 int ops)
             else if (OP == 1) v[i] = __viaddmin_u16x2(v[i], a, b + i); // VIADDMNMX.U16x2 (4 int16 ops: 2 adds + 2 mins)
             else if (OP == 2) v[i] = __popc(v[i] ^ a) + b;             // LOP3 + POPC + IADD
-            else v[i] = __vminu2(v[i] + a, b);                         // IADD + VIMNMX.U16x2
+            else if (OP == 3) v[i] = __vminu2(v[i] + a, b);            // IADD + VIMNMX.U16x2
+            else if (OP == 4) v[i] = __vminu2(__vmaxu2(v[i], a + i), b + it);  // 2 x VIMNMX.U16x2 (packed min / max alone)
+            else v[i] = __vimin3_u16x2(v[i] ^ a, b + i, a + it);       // LOP3 + VIMNMX3.U16x2
         }
     }
     unsigned s = 0;
@@ -54,11 +56,13 @@ int main() {
     unsigned* out;
     cudaMalloc(&out, (size_t)blocks * 256 * 4);
     const double r0 = run<0>(out, blocks), r1 = run<1>(out, blocks), r2 = run<2>(out, blocks), r3 = run<3>(out, blocks);
+    const double r4 = run<4>(out, blocks), r5 = run<5>(out, blocks);
     printf("{\"gpu\": \"%s\", \"sms\": %d, \"how\": \"tools/int_peak.cu: ILP-%d register-only loops, 8 CTAs x 256 threads per SM, best of 5, CUDA events\",\n",
            p.name, p.multiProcessorCount, ILP);
     printf(" \"int32_add_logic_gops\": %.1f,\n", 2 * r0 / 1e9);
     printf(" \"dpx_viaddmnmx_u16x2_inst_ginst\": %.1f, \"dpx_viaddmnmx_u16x2_int16_gops\": %.1f,\n", r1 / 1e9, 4 * r1 / 1e9);
     printf(" \"popc_xor_add_gops\": %.1f, \"popc_ginst\": %.1f,\n", 3 * r2 / 1e9, r2 / 1e9);
-    printf(" \"iadd_vimnmx_u16x2_ginst\": %.1f}\n", 2 * r3 / 1e9);
+    printf(" \"iadd_vimnmx_u16x2_ginst\": %.1f,\n", 2 * r3 / 1e9);
+    printf(" \"vimnmx_u16x2_ginst\": %.1f, \"lop3_vimnmx3_u16x2_ginst\": %.1f}\n", 2 * r4 / 1e9, 2 * r5 / 1e9);
     return 0;
 }
