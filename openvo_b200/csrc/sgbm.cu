@@ -466,8 +466,14 @@ template <int LPC, int VG>
 __host__ __device__ constexpr int vs_tile() { return VG * vs_cpw<LPC>(); }
 template <int LPC, int BR, int VG>
 __host__ __device__ constexpr int vs_diag_groups() { return VG + BR / vs_cpw<LPC>(); }
+#ifndef OVO_VS_NSLOT
+#define OVO_VS_NSLOT 2
+#endif
+constexpr int kVsSlots = OVO_VS_NSLOT;  // line groups per warp
 template <int LPC, int BR, int VG>
-__host__ __device__ constexpr int vs_warps() { return (VG + 2 * vs_diag_groups<LPC, BR, VG>()) / 2; }
+__host__ __device__ constexpr int vs_groups() { return VG + 2 * vs_diag_groups<LPC, BR, VG>(); }
+template <int LPC, int BR, int VG>
+__host__ __device__ constexpr int vs_warps() { return (vs_groups<LPC, BR, VG>() + kVsSlots - 1) / kVsSlots; }
 #ifndef OVO_VS_MINB
 #define OVO_VS_MINB 2
 #endif
@@ -622,11 +628,14 @@ __global__ void __launch_bounds__(32 * vs_warps<LPC, BR, VG>(), vs_ctas_per_sm<L
     PathLane<LPC> pl;
     pl.init(lane);
 
-    VsSlot<NPR> sl[2];
-    int x[2];  // column of this lane's cell at the band's first row
+    VsSlot<NPR> sl[kVsSlots];
+    int x[kVsSlots];  // column of this lane's cell at the band's first row
+    bool live[kVsSlots];
 #pragma unroll
-    for (int k = 0; k < 2; k++) {
-        const int gid = wid + k * NWARP;
+    for (int k = 0; k < kVsSlots; k++) {
+        constexpr int NG = vs_groups<LPC, BR, VG>();
+        const int gid = min(wid + k * NWARP, NG - 1);  // a surplus slot recomputes the last group and stores nothing
+        live[k] = NG % kVsSlots == 0 || wid + k * NWARP < NG;
         int xs, dx;
         if (gid < VG) { sl[k].kind = 0; dx = 0; xs = x0 + gid * CPW; }
         else if (gid < VG + NDG) { sl[k].kind = 1; dx = 1; xs = x0 - BR + (gid - VG) * CPW; }
@@ -665,18 +674,18 @@ __global__ void __launch_bounds__(32 * vs_warps<LPC, BR, VG>(), vs_ctas_per_sm<L
 #ifndef OVO_EMU
         if (t < R) mbar_wait(&bar[t % kVsStrips], (t / kVsStrips) & 1);
 #endif
-        bool act[2], mine[2];
-        uint32_t c[2][NPR];
+        bool act[kVsSlots], mine[kVsSlots];
+        uint32_t c[kVsSlots][NPR];
 #pragma unroll
-        for (int k = 0; k < 2; k++) {
+        for (int k = 0; k < kVsSlots; k++) {
             const int r = t - sl[k].kind;
             act[k] = !CHECK || (r >= 0 && r < R);
             if (act[k]) ldv<NPR>(c[k], strips + sl[k].sbase + sl[k].scol);
         }
 #pragma unroll
-        for (int k = 0; k < 2; k++) {
+        for (int k = 0; k < kVsSlots; k++) {
             if (!act[k]) continue;
-            mine[k] = (unsigned)(sl[k].scol - mine_lo) < (unsigned)(B * DH);
+            mine[k] = live[k] && (unsigned)(sl[k].scol - mine_lo) < (unsigned)(B * DH);
             if (EDGE) {
                 const int xc = x[k] + (sl[k].dcol / DH) * (t - sl[k].kind);
                 // a diagonal line enters the image here: its predecessor lies outside (all-zero vector)
@@ -686,7 +695,7 @@ __global__ void __launch_bounds__(32 * vs_warps<LPC, BR, VG>(), vs_ctas_per_sm<L
             path_step<LPC, NPR, PAD>(sl[k].s, c[k], padmask, P1P1, P2P2, pl);
         }
 #pragma unroll
-        for (int k = 0; k < 2; k++) {
+        for (int k = 0; k < kVsSlots; k++) {
             if (!act[k]) continue;
             if (mine[k]) {
                 vs_meet<LPC, NPR, BR, SAT>(sl[k], q, ring, Sv);
