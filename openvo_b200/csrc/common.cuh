@@ -22,6 +22,31 @@ void prof_post(cudaStream_t st);
 #include <cstddef>
 #include <cstdio>
 
+// Debug build (-DOVO_BOUNDS, openvo_b200.build.build_variant("bounds", ["OVO_BOUNDS"])): every computed shared / global
+// offset of the SGBM kernels is checked on the device; a violation prints its site and traps (the stream then reports an error).
+// The GPU parity tests are run once per round against that variant (tools/bounds_check.sh) in place of compute-sanitizer.
+#if defined(OVO_BOUNDS) && defined(OVO_EMU)
+#include <cstdlib>
+#define OVO_DEVCHECK(cond)                                                         \
+    do {                                                                           \
+        if (!(cond)) {                                                             \
+            fprintf(stderr, "OVO_BOUNDS %s:%d: %s\n", __FILE__, __LINE__, #cond); \
+            std::abort();                                                          \
+        }                                                                          \
+    } while (0)
+#elif defined(OVO_BOUNDS)
+#define OVO_DEVCHECK(cond)                                                                                         \
+    do {                                                                                                           \
+        if (!(cond)) {                                                                                             \
+            printf("OVO_BOUNDS %s:%d block (%d,%d,%d) thread %d: %s\n", __FILE__, __LINE__, (int)blockIdx.x, (int)blockIdx.y, \
+                   (int)blockIdx.z, (int)threadIdx.x, #cond);                                                      \
+            __trap();                                                                                              \
+        }                                                                                                          \
+    } while (0)
+#else
+#define OVO_DEVCHECK(cond) ((void)0)
+#endif
+
 namespace ovo {
 
 // ---- error plumbing -------------------------------------------------------------------------------------

@@ -133,6 +133,8 @@ __device__ __forceinline__ void cost_row(const uint2* __restrict__ Lrow, const u
         uint32_t pix = 0;
         if (!PAD || !pad) {
             uint2 lw, r0, r1;
+            OVO_DEVCHECK(x0 + j + D - dhi >= 0 || EDGE);
+            OVO_DEVCHECK((EDGE ? min(x0 + j, W1 - 1) : x0 + j) + D < W1 + D && dlo <= dhi && dhi < D);
             if (EDGE) {
                 const int xx = min(max(x0 + j, 0), W1 - 1);
                 lw = __ldg(Lrow + xx + D);
@@ -515,6 +517,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
 }
 #endif
 
+constexpr size_t kStripSlackFront = 8 * 1024, kStripSlackBack = 32 * 1024;  // see sgbm_workspace_bytes
 constexpr int kVsRing = 3;    // rows of the shared-memory ring in which the three directions of a cell meet
 constexpr int kVsStrips = 5;  // C strips in shared memory: rows t-2 .. t in use, rows t+1 and t+2 in flight
 
@@ -578,6 +581,7 @@ __global__ void __launch_bounds__(32 * vs_warps<LPC, BR, VG>(), vs_ctas_per_sm<L
     constexpr int CPW = vs_cpw<LPC>(), B = vs_tile<LPC, VG>(), DH = LPC * NPR, NDG = vs_diag_groups<LPC, BR, VG>(), NWARP = vs_warps<LPC, BR, VG>();
     constexpr int SW = B + 2 * BR;  // cells of a C strip: the tile and the halo on both sides
     static_assert(NPR % 4 == 0, "128-bit accesses");
+    static_assert((size_t)BR * DH * 4 <= kStripSlackFront && (size_t)(B + BR) * DH * 4 <= kStripSlackBack, "strip overhang vs workspace slack");
     OVO_DYN_SMEM(uint32_t, smem);
     uint32_t* strips = smem;                           // [kVsStrips][SW][DH]  (first: the bulk copies want 16-byte alignment)
     uint32_t* ring = smem + kVsStrips * SW * DH;       // [kVsRing][B][DH]
@@ -602,6 +606,10 @@ __global__ void __launch_bounds__(32 * vs_warps<LPC, BR, VG>(), vs_ctas_per_sm<L
         if (rn >= R) return;
         const uint32_t* src = strip_src + (ptrdiff_t)rn * W1 * DH;
         uint32_t* dst = strips + (rn % kVsStrips) * SW * DH;
+        // the copy may run over the ends of C, never out of the frame's workspace (sgbm_workspace_bytes)
+        OVO_DEVCHECK(src >= reinterpret_cast<const uint32_t*>(frame_ptr(ws.prep, ws_stride, f)) &&
+                     src + SW * DH <= reinterpret_cast<const uint32_t*>(frame_ptr(ws.prep, ws_stride, f)) + ws_stride / 4);
+        OVO_DEVCHECK((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0);
 #ifndef OVO_EMU
         if (threadIdx.x == 0) {
             mbar_expect_tx(&bar[rn % kVsStrips], SW * DH * 4);
@@ -680,7 +688,10 @@ __global__ void __launch_bounds__(32 * vs_warps<LPC, BR, VG>(), vs_ctas_per_sm<L
         for (int k = 0; k < kVsSlots; k++) {
             const int r = t - sl[k].kind;
             act[k] = !CHECK || (r >= 0 && r < R);
-            if (act[k]) ldv<NPR>(c[k], strips + sl[k].sbase + sl[k].scol);
+            if (act[k]) {
+                OVO_DEVCHECK(sl[k].scol >= 0 && sl[k].scol + NPR <= SW * DH && sl[k].sbase == (r % kVsStrips) * SW * DH);
+                ldv<NPR>(c[k], strips + sl[k].sbase + sl[k].scol);
+            }
         }
 #pragma unroll
         for (int k = 0; k < kVsSlots; k++) {
@@ -698,9 +709,14 @@ __global__ void __launch_bounds__(32 * vs_warps<LPC, BR, VG>(), vs_ctas_per_sm<L
         for (int k = 0; k < kVsSlots; k++) {
             if (!act[k]) continue;
             if (mine[k]) {
+                OVO_DEVCHECK(sl[k].rbase == ((t - sl[k].kind) % kVsRing) * B * DH && sl[k].scol - mine_lo >= 0 &&
+                             sl[k].scol - mine_lo + DH - q * NPR <= B * DH);
+                OVO_DEVCHECK(sl[k].off >= 0 && (size_t)sl[k].off + NPR <= vol &&
+                             sl[k].off == (int32_t)(((ptrdiff_t)(y0 + t - sl[k].kind) * W1 + x[k] + (sl[k].dcol / DH) * (t - sl[k].kind)) * DH + q * NPR));
                 vs_meet<LPC, NPR, BR, SAT>(sl[k], q, ring, Sv);
                 if (CHECK && t - sl[k].kind == R - 1) {
                     const int xc = x[k] + (sl[k].dcol / DH) * (R - 1);
+                    OVO_DEVCHECK(xc >= 0 && xc < W1);
                     stv<NPR>(bb_out + ((size_t)sl[k].kind * W1 + xc) * DH + q * NPR, sl[k].s.L);
                 }
             }
@@ -863,6 +879,7 @@ struct HorizRow {          // per-thread view of one row
     uint32_t* ck_own;      // checkpoints of this warp's phase-1 sweep (segment j at j * 32*NPR words)
     const uint32_t* ck_oth;
     int xa, n1, n2;        // first cell and length of the own phase-1 sweep; length of the other warp's
+    int sph;               // checkpoint slots per half row
     uint32_t *selA, *selB;
     uint16_t* selBest;
     uint32_t* svec;        // this warp's shared-memory slots for the K cost vectors of a segment
@@ -893,12 +910,14 @@ __device__ __forceinline__ void horiz_phase1(const SgbmDims& d, const HorizRow<N
 #pragma unroll
             for (int i = 0; i < PF; i++) {
                 if (i % K == 0) {
+                    OVO_DEVCHECK(pk >= R.ck_own && pk - R.ck_own < (ptrdiff_t)R.sph * WPC);
                     if (k + i) stv<NPR>(pk, s.L);
                     pk += WPC;
                 }
                 uint32_t c[NPR];
 #pragma unroll
                 for (int r = 0; r < NPR; r++) c[r] = cb[i][r];
+                OVO_DEVCHECK(R.xa + DIRX * (k + i + PF) >= 0 && R.xa + DIRX * (k + i + PF) < d.W1);
                 ldv<NPR>(cb[i], pc + i * DS);
                 path_step<32, NPR, PAD>(s, c, padmask, P1P1, P2P2, pl);
             }
@@ -907,6 +926,7 @@ __device__ __forceinline__ void horiz_phase1(const SgbmDims& d, const HorizRow<N
             for (int i = 0; i < PF; i++) {
                 if (k + i < n1) {
                     if (i % K == 0) {
+                        OVO_DEVCHECK(pk >= R.ck_own && pk - R.ck_own < (ptrdiff_t)R.sph * WPC);
                         if (k + i) stv<NPR>(pk, s.L);
                         pk += WPC;
                     }
@@ -951,6 +971,8 @@ __device__ __forceinline__ void horiz_segment(const SgbmDims& d, const HorizRow<
     // the other warp's cell k (counted along ITS sweep) sits at x = xo - DIRX * k
     const int xo = (DIRX > 0 ? d.W1 - 1 : 0) - DIRX * (j * K);
     const ptrdiff_t o0 = (ptrdiff_t)xo * WPC;  // cell i of the segment is at o0 - i * DS
+    OVO_DEVCHECK(xo >= 0 && xo < d.W1 && xo - DIRX * ((FULL ? K : cnt) - 1) >= 0 && xo - DIRX * ((FULL ? K : cnt) - 1) < d.W1);
+    OVO_DEVCHECK(j == 0 || (xo + DIRX * K >= 0 && xo + DIRX * K < d.W1 && xo + DIRX >= 0 && xo + DIRX < d.W1 && j < R.sph));
     uint32_t sv[K][NPR];
     {
         // replay the other warp's path over the segment
@@ -1094,6 +1116,7 @@ __global__ void __launch_bounds__(64, NPR == 4 ? 6 : OVO_HOR_MINB) k_sgbm_horiz(
     R.xa = wid == 0 ? 0 : W1 - 1;
     R.n1 = wid == 0 ? mid : W1 - mid;
     R.n2 = W1 - R.n1;
+    R.sph = sph;
     R.selA = selA; R.selB = selB; R.selBest = selBest;
     R.svec = svec_s[wid];
 
@@ -1114,6 +1137,7 @@ __global__ void __launch_bounds__(64, NPR == 4 ? 6 : OVO_HOR_MINB) k_sgbm_horiz(
             const bool reject = fac > 0 ? (m2 * fac < minS * 100) : (m2 == 0);
             if (reject) continue;
             const int x = x1 + D;
+            OVO_DEVCHECK(best >= 0 && best < D);
             if (minS < 32767) atomicMin(&d2key[x - best], ((uint32_t)minS << 16) | (uint32_t)(0xFFFF - best));
             int dsp = best * 16;
             if (best > 0 && best < D - 1) {
@@ -1387,17 +1411,26 @@ static size_t lv_bytes(const SgbmDims& d) {
     return (d.mode ? 6 : 3) * vol;
 }
 
+// The fused vertical kernel copies C by row strips that overhang the tile by BR cells on the left and up to a tile + BR cells on
+// the right (k_sgbm_vsum: fetch), i.e. up to 8 KB before C and 32 KB behind it; the overhang is never used, but it must be the
+// frame's own memory even for images of a few rows, hence a floor under the region in front of C and a tail behind the frame.
+static size_t prep_bytes(const SgbmDims& d) {
+    const size_t img = align_up((size_t)d.H * d.W * 4, 256);
+    return 4 * img > kStripSlackFront ? 4 * img : kStripSlackFront;
+}
+
 size_t sgbm_workspace_bytes(const SgbmDims& d) {
     const size_t vol = align_up((size_t)d.H * d.W1 * d.Dp * 2, 256);
     const size_t img = align_up((size_t)d.H * d.W * 4, 256);
-    return align_up(4 * img /*prep*/ + vol /*C*/ + lv_bytes(d) + ckpt_bytes(d) + 4 * img /*raw, med (i16) + label, csize (i32) -> 2*0.5+2 = 3 img*/, 256);
+    return align_up(prep_bytes(d) + vol /*C*/ + lv_bytes(d) + ckpt_bytes(d) + 4 * img /*raw, med (i16) + label, csize (i32) -> 2*0.5+2 = 3 img*/ +
+                        kStripSlackBack, 256);
 }
 
 void sgbm_carve(const SgbmDims& d, uint8_t* base, SgbmWorkspace* ws) {
     const size_t vol = align_up((size_t)d.H * d.W1 * d.Dp * 2, 256);
     const size_t img = align_up((size_t)d.H * d.W * 4, 256);
     uint8_t* p = base;
-    ws->prep = reinterpret_cast<uint32_t*>(p); p += 4 * img;
+    ws->prep = reinterpret_cast<uint32_t*>(p); p += prep_bytes(d);
     ws->C = reinterpret_cast<int16_t*>(p); p += vol;
     ws->Lv = reinterpret_cast<int16_t*>(p); p += lv_bytes(d);
     ws->ckpt = reinterpret_cast<int16_t*>(p); p += ckpt_bytes(d);

@@ -1,5 +1,6 @@
 """TEST INFRASTRUCTURE ONLY: compile openvo_b200/csrc/*.cu with g++ against tests/emu/cuda_emu.h so the kernels' logic can be
-exercised in the CPU-only tier.  The product never loads this library (openvo_b200/_native.py only loads the nvcc build)."""
+exercised in the CPU-only tier.  The product never loads this library (openvo_b200/_native.py only loads the nvcc build).
+Built with -DOVO_BOUNDS: the kernels' own offset checks (OVO_DEVCHECK, csrc/common.cuh) abort the test process when violated."""
 import os
 import subprocess
 
@@ -21,7 +22,7 @@ def build(force=False):
             src = os.path.join(CSRC, f)
             if force or not os.path.exists(obj) or any(os.path.getmtime(d) > os.path.getmtime(obj) for d in deps):
                 subprocess.check_call(["g++", "-std=c++17", "-O2", "-g", "-DOVO_EMU", "-I", HERE, "-fPIC", "-mfma",
-                                       "-ffp-contract=off", "-Wno-unused-function"] + os.environ.get("OVO_EMU_DEFS", "").split() + [ "-x", "c++", "-c", src, "-o", obj])
+                                       "-ffp-contract=off", "-Wno-unused-function"] + os.environ.get("OVO_EMU_DEFS", "-DOVO_BOUNDS").split() + [ "-x", "c++", "-c", src, "-o", obj])
             objs.append(obj)
         subprocess.check_call(["g++", "-shared", "-o", OUT] + objs + ["-lpthread"])
     return OUT
