@@ -456,8 +456,11 @@ __global__ void __launch_bounds__(256) k_sgbm_vert(SgbmDims d, SgbmWorkspace ws,
 // A tile has 16 V groups (B = 16 * CPW columns) and 16 + BR / CPW groups per diagonal direction: the extra ones start in the
 // BR columns beside the tile and are only there to carry the state of the lines that enter the tile further down (the halo is
 // recomputed instead of exchanged between CTAs, so a band is ONE launch without inter-CTA synchronisation).  Every warp owns two
-// groups.  Rows are software-pipelined over a three-row shared-memory ring: in iteration t the V groups store L2 of row t, the
-// D1 groups add L1 to row t-1 and the D3 groups add L3 to row t-2 and write the finished sum to Sv; one barrier per iteration.
+// groups of the same direction and walks the band's rows at its own pace.  The three directions of a cell meet in a three-row
+// shared-memory ring: the V warps store L2 of row r, the D1 warps add L1, the D3 warps add L3 and write the finished sum to
+// Sv.  The hand-overs are producer / consumer named barriers (bar.arrive by the warps that wrote, bar.sync by the warps that
+// read; one barrier per edge V->D1, D1->D3, D3->V and ring row), never a CTA-wide barrier, so the warps of one direction may
+// run up to a few rows ahead of the next one and their shared-memory and arithmetic phases overlap instead of alternating.
 // The state of the lines at the last row of the band goes to a small buffer (3 x W1 vectors per frame and parity) from which
 // the next band's launch starts, so path state never leaves registers inside a band and Sv is the only volume written.
 // ------------------------------------------------------------------------------------------------------------
@@ -468,14 +471,11 @@ template <int LPC, int VG>
 __host__ __device__ constexpr int vs_tile() { return VG * vs_cpw<LPC>(); }
 template <int LPC, int BR, int VG>
 __host__ __device__ constexpr int vs_diag_groups() { return VG + BR / vs_cpw<LPC>(); }
-#ifndef OVO_VS_NSLOT
-#define OVO_VS_NSLOT 2
-#endif
-constexpr int kVsSlots = OVO_VS_NSLOT;  // line groups per warp
+constexpr int kVsSlots = 2;  // line groups per warp (both of the warp's direction)
 template <int LPC, int BR, int VG>
 __host__ __device__ constexpr int vs_groups() { return VG + 2 * vs_diag_groups<LPC, BR, VG>(); }
 template <int LPC, int BR, int VG>
-__host__ __device__ constexpr int vs_warps() { return (vs_groups<LPC, BR, VG>() + kVsSlots - 1) / kVsSlots; }
+__host__ __device__ constexpr int vs_warps() { return vs_groups<LPC, BR, VG>() / kVsSlots; }
 #ifndef OVO_VS_MINB
 #define OVO_VS_MINB 2
 #endif
@@ -517,20 +517,34 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
 }
 #endif
 
+// producer / consumer named barriers (ids 1..15; 0 is __syncthreads): count = threads of the warps that arrive + of those that wait
+#ifndef OVO_EMU
+__device__ __forceinline__ void nbar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void nbar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+#else
+__device__ __forceinline__ void nbar_arrive(int id, int count) { ovo_emu::named_barrier(id, count, false); }
+__device__ __forceinline__ void nbar_sync(int id, int count) { ovo_emu::named_barrier(id, count, true); }
+#endif
+
 constexpr size_t kStripSlackFront = 8 * 1024, kStripSlackBack = 32 * 1024;  // see sgbm_workspace_bytes
-constexpr int kVsRing = 3;    // rows of the shared-memory ring in which the three directions of a cell meet
-constexpr int kVsStrips = 5;  // C strips in shared memory: rows t-2 .. t in use, rows t+1 and t+2 in flight
+#ifndef OVO_VS_RING
+#define OVO_VS_RING 3
+#endif
+#ifndef OVO_VS_AHEAD
+#define OVO_VS_AHEAD 1
+#endif
+constexpr int kVsRing = OVO_VS_RING;    // rows of the shared-memory ring in which the three directions of a cell meet: the V warps may
+                                        // be this many rows ahead of the D3 warps
+constexpr int kVsAhead = OVO_VS_AHEAD;  // the strip of row r + kVsAhead is requested when the first V warp starts row r
+constexpr int kVsStrips = kVsRing + kVsAhead;  // C strips in shared memory: rows r - kVsRing + 1 .. r in use, kVsAhead more in flight
+static_assert(3 * kVsRing <= 15, "named barriers 1 .. 15");
 
 template <int NPR>
 struct VsSlot {
     PathState<NPR> s;
-    int kind;       // 0 = V, 1 = D1, 2 = D3 (also the pipeline delay in rows)
-    int dcol;       // words the slot's cell moves along a row of the strip / ring per image row: dx * DH
+    int x;          // column of this lane's cell at the band's first row
     int scol;       // word offset of this lane's words inside a strip row: (x - (x0 - BR)) * DH + q * NPR
-    int sbase;      // word offset of the current row's strip:  (r % kVsStrips) * SW * DH
-    int rbase;      // word offset of the current row in the ring: (r % kVsRing) * B * DH
     int32_t off;    // word offset of this lane's words in Sv for the current row (a frame's volume is < 2^31 words)
-    int32_t step;   // ... and its increment per row: (W1 + dx) * DH
 };
 
 // shared-memory position (in words) of chunk i (4 words) of lane q inside a cell of the ring: for a fixed i the lanes of a cell
@@ -538,15 +552,13 @@ struct VsSlot {
 template <int LPC>
 __device__ __forceinline__ int vs_chunk(int q, int i) { return (i * LPC + q) * 4; }
 
-// The three directions of a cell meet in the ring: V stores, D1 adds, D3 adds and writes the sum to Sv.
-template <int LPC, int NPR, int BR, bool SAT>
-__device__ __forceinline__ void vs_meet(const VsSlot<NPR>& sl, int q, uint32_t* ring, uint32_t* __restrict__ Sv) {
-    constexpr int DH = LPC * NPR;
-    uint32_t* cell = ring + sl.rbase + (sl.scol - (BR * DH + q * NPR));
-    if (sl.kind == 0) {
+// The three directions of a cell meet in the ring: V (KIND 0) stores, D1 (1) adds, D3 (2) adds and writes the sum to Sv.
+template <int KIND, int LPC, int NPR, bool SAT>
+__device__ __forceinline__ void vs_meet(const PathState<NPR>& st, uint32_t* cell, int q, uint32_t* __restrict__ sv) {
+    if (KIND == 0) {
 #pragma unroll
         for (int i = 0; i < NPR / 4; i++)
-            *reinterpret_cast<uint4*>(cell + vs_chunk<LPC>(q, i)) = make_uint4(sl.s.L[4 * i], sl.s.L[4 * i + 1], sl.s.L[4 * i + 2], sl.s.L[4 * i + 3]);
+            *reinterpret_cast<uint4*>(cell + vs_chunk<LPC>(q, i)) = make_uint4(st.L[4 * i], st.L[4 * i + 1], st.L[4 * i + 2], st.L[4 * i + 3]);
     } else {
         uint32_t a[NPR];
 #pragma unroll
@@ -555,32 +567,25 @@ __device__ __forceinline__ void vs_meet(const VsSlot<NPR>& sl, int q, uint32_t* 
             a[4 * i] = v.x; a[4 * i + 1] = v.y; a[4 * i + 2] = v.z; a[4 * i + 3] = v.w;
         }
 #pragma unroll
-        for (int k = 0; k < NPR; k++) a[k] = sum16<SAT>(a[k], sl.s.L[k]);
-        if (sl.kind == 1) {
+        for (int k = 0; k < NPR; k++) a[k] = sum16<SAT>(a[k], st.L[k]);
+        if (KIND == 1) {
 #pragma unroll
             for (int i = 0; i < NPR / 4; i++)
                 *reinterpret_cast<uint4*>(cell + vs_chunk<LPC>(q, i)) = make_uint4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
         } else {
-            stv<NPR>(Sv + sl.off, a);
+            stv<NPR>(sv, a);
         }
     }
-}
-
-template <int LPC, int NPR, int BR, int VG>
-__device__ __forceinline__ void vs_advance(VsSlot<NPR>& sl) {
-    constexpr int B = vs_tile<LPC, VG>(), DH = LPC * NPR, SW = B + 2 * BR;
-    sl.scol += sl.dcol;
-    sl.off += sl.step;
-    sl.sbase = sl.sbase == (kVsStrips - 1) * SW * DH ? 0 : sl.sbase + SW * DH;
-    sl.rbase = sl.rbase == (kVsRing - 1) * B * DH ? 0 : sl.rbase + B * DH;
 }
 
 template <int LPC, int NPR, bool PAD, int BR, int VG, bool SAT>
 __global__ void __launch_bounds__(32 * vs_warps<LPC, BR, VG>(), vs_ctas_per_sm<LPC, BR, VG>())
     k_sgbm_vsum(SgbmDims d, SgbmWorkspace ws, size_t ws_stride, int y0, int parity) {
-    constexpr int CPW = vs_cpw<LPC>(), B = vs_tile<LPC, VG>(), DH = LPC * NPR, NDG = vs_diag_groups<LPC, BR, VG>(), NWARP = vs_warps<LPC, BR, VG>();
+    constexpr int CPW = vs_cpw<LPC>(), B = vs_tile<LPC, VG>(), DH = LPC * NPR, NDG = vs_diag_groups<LPC, BR, VG>();
     constexpr int SW = B + 2 * BR;  // cells of a C strip: the tile and the halo on both sides
+    constexpr int WV = VG / kVsSlots, WD = NDG / kVsSlots;  // warps per direction
     static_assert(NPR % 4 == 0, "128-bit accesses");
+    static_assert(VG % kVsSlots == 0 && NDG % kVsSlots == 0, "a warp's groups are of one direction");
     static_assert((size_t)BR * DH * 4 <= kStripSlackFront && (size_t)(B + BR) * DH * 4 <= kStripSlackBack, "strip overhang vs workspace slack");
     OVO_DYN_SMEM(uint32_t, smem);
     uint32_t* strips = smem;                           // [kVsStrips][SW][DH]  (first: the bulk copies want 16-byte alignment)
@@ -602,7 +607,10 @@ __global__ void __launch_bounds__(32 * vs_warps<LPC, BR, VG>(), vs_ctas_per_sm<L
     // strip of band row rn: cells [x0 - BR, x0 + B + BR) of image row y0 + rn (running over the row ends into the neighbouring
     // rows; the frame's workspace surrounds C, so the source is always valid memory, and those cells are never stored)
     const uint32_t* strip_src = C + ((ptrdiff_t)y0 * W1 + (x0 - BR)) * DH;
-    auto fetch = [&](int rn) {
+#ifdef OVO_EMU
+    __shared__ volatile int emu_landed[kVsStrips];  // image row whose strip sits in each slot (stands in for the mbarrier phase)
+#endif
+    auto fetch = [&](int rn) {  // thread 0 only
         if (rn >= R) return;
         const uint32_t* src = strip_src + (ptrdiff_t)rn * W1 * DH;
         uint32_t* dst = strips + (rn % kVsStrips) * SW * DH;
@@ -611,12 +619,11 @@ __global__ void __launch_bounds__(32 * vs_warps<LPC, BR, VG>(), vs_ctas_per_sm<L
                      src + SW * DH <= reinterpret_cast<const uint32_t*>(frame_ptr(ws.prep, ws_stride, f)) + ws_stride / 4);
         OVO_DEVCHECK((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0);
 #ifndef OVO_EMU
-        if (threadIdx.x == 0) {
-            mbar_expect_tx(&bar[rn % kVsStrips], SW * DH * 4);
-            bulk_g2s(dst, src, SW * DH * 4, &bar[rn % kVsStrips]);
-        }
+        mbar_expect_tx(&bar[rn % kVsStrips], SW * DH * 4);
+        bulk_g2s(dst, src, SW * DH * 4, &bar[rn % kVsStrips]);
 #else
-        for (int i = threadIdx.x; i < SW * DH; i += blockDim.x) dst[i] = src[i];
+        for (int i = 0; i < SW * DH; i++) dst[i] = src[i];  // the copy engine, emulated: done at once
+        emu_landed[rn % kVsStrips] = rn;
 #endif
     };
 #ifndef OVO_EMU
@@ -625,116 +632,120 @@ __global__ void __launch_bounds__(32 * vs_warps<LPC, BR, VG>(), vs_ctas_per_sm<L
         for (int i = 0; i < kVsStrips; i++) mbar_init(&bar[i], 1);
         mbar_fence_init();
     }
-    __syncthreads();
+#else
+    if (threadIdx.x == 0)
+        for (int i = 0; i < kVsStrips; i++) emu_landed[i] = -1;
 #endif
-    fetch(0);
-    fetch(1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kVsAhead; i++) fetch(i);
+    }
 
     uint32_t padmask[NPR];
     make_padmask<LPC, NPR>(padmask, lane, d.D);
     const uint32_t P1P1 = bcast16(d.P1), P2P2 = bcast16(d.P2);
     PathLane<LPC> pl;
     pl.init(lane);
-
-    VsSlot<NPR> sl[kVsSlots];
-    int x[kVsSlots];  // column of this lane's cell at the band's first row
-    bool live[kVsSlots];
-#pragma unroll
-    for (int k = 0; k < kVsSlots; k++) {
-        constexpr int NG = vs_groups<LPC, BR, VG>();
-        const int gid = min(wid + k * NWARP, NG - 1);  // a surplus slot recomputes the last group and stores nothing
-        live[k] = NG % kVsSlots == 0 || wid + k * NWARP < NG;
-        int xs, dx;
-        if (gid < VG) { sl[k].kind = 0; dx = 0; xs = x0 + gid * CPW; }
-        else if (gid < VG + NDG) { sl[k].kind = 1; dx = 1; xs = x0 - BR + (gid - VG) * CPW; }
-        else { sl[k].kind = 2; dx = -1; xs = x0 + (gid - VG - NDG) * CPW; }
-        x[k] = xs + g;
-        sl[k].dcol = dx * DH;
-        sl[k].scol = (x[k] - (x0 - BR)) * DH + q * NPR;
-        sl[k].sbase = 0;
-        sl[k].rbase = 0;
-        sl[k].off = (int32_t)(((ptrdiff_t)y0 * W1 + x[k]) * DH + q * NPR);
-        sl[k].step = (W1 + dx) * DH;
-        // state of the predecessor cell (x - dx, y0 - 1), or the all-zero vector when it lies outside the image
-        const int xp = x[k] - dx;
-        const bool have = y0 > 0 && xp >= 0 && xp < W1;
-        uint32_t v[NPR];
-#pragma unroll
-        for (int r = 0; r < NPR; r++) v[r] = 0;
-        if (have) ldv<NPR>(v, bb_in + ((size_t)sl[k].kind * W1 + xp) * DH + q * NPR);
-#pragma unroll
-        for (int r = 0; r < NPR; r++) sl[k].s.L[r] = v[r];
-        sl[k].s.mm = vec_min<LPC, NPR>(sl[k].s.L, pl);
-    }
     const bool edge = x0 - BR <= 0 || x0 + B + BR >= W1;  // diagonal lines of this tile can start at the image border
-#ifdef OVO_EMU
-    __syncthreads();
-#endif
-    const int mine_lo = BR * DH + q * NPR;  // scol of the tile's first column for this lane
+    const int mine_lo = BR * DH + q * NPR;                // scol of the tile's first column for this lane
 
-    // iteration t: slot k computes row t - kind; the strip of row t + 2 is requested, that of row t must have landed.
-    // CHECK: some slot may be outside the band or on its last row (state hand-over); EDGE: the tile touches the image border
-    // (diagonal lines start there; cells beyond the border are computed on whatever the strip holds and never stored).
-    // The plain variant is straight-line for both slots, so that the two recurrences interleave.
-    auto iteration = [&](int t, auto check, auto edge_t) {
-        constexpr bool CHECK = decltype(check)::value, EDGE = decltype(edge_t)::value;
-        fetch(t + 2);
+    // One direction: KIND 0 = V (dx 0), 1 = D1 (dx +1), 2 = D3 (dx -1); gw = the warp's index among the warps of its direction.
+    // Barrier ids (i = ring row): 1 + i: V stored ring row i;  1 + kVsRing + i: D1 added to it;  1 + 2 kVsRing + i: D3 is done with it
+    // (and with the strip of the same image row, whose slot the copy of row r + kVsAhead then reuses).
+    auto run = [&](auto kind_t, auto edge_t, int gw) {
+        constexpr int KIND = decltype(kind_t)::value;
+        constexpr bool EDGE = decltype(edge_t)::value;
+        constexpr int DX = KIND == 0 ? 0 : KIND == 1 ? 1 : -1;
+        constexpr int NA = (WV + WD) * 32, NB = 2 * WD * 32, NC = (WD + WV) * 32;
+        VsSlot<NPR> sl[kVsSlots];
+#pragma unroll
+        for (int k = 0; k < kVsSlots; k++) {
+            const int gi = gw * kVsSlots + k;  // group of this direction
+            const int xs = KIND == 1 ? x0 - BR + gi * CPW : x0 + gi * CPW;
+            sl[k].x = xs + g;
+            sl[k].scol = (sl[k].x - (x0 - BR)) * DH + q * NPR;
+            sl[k].off = (int32_t)(((ptrdiff_t)y0 * W1 + sl[k].x) * DH + q * NPR);
+            // state of the predecessor cell (x - dx, y0 - 1), or the all-zero vector when it lies outside the image
+            const int xp = sl[k].x - DX;
+            const bool have = y0 > 0 && xp >= 0 && xp < W1;
+            uint32_t v[NPR];
+#pragma unroll
+            for (int r = 0; r < NPR; r++) v[r] = 0;
+            if (have) ldv<NPR>(v, bb_in + ((size_t)KIND * W1 + xp) * DH + q * NPR);
+#pragma unroll
+            for (int r = 0; r < NPR; r++) sl[k].s.L[r] = v[r];
+            sl[k].s.mm = vec_min<LPC, NPR>(sl[k].s.L, pl);
+        }
+        int sbase = 0, rbase = 0, ri = 0;  // strip / ring row of the current image row, r % kVsRing
+#pragma unroll 1
+        for (int r = 0; r < R; r++) {
+            if (KIND == 0) {
+                // ring row r % kVsRing and the strip slot of row r + kVsAhead were last used for row r - kVsRing: wait until D3 is done with it
+                if (r >= kVsRing) nbar_sync(1 + 2 * kVsRing + ri, NC);
+                if (threadIdx.x == 0) fetch(r + kVsAhead);
+            }
 #ifndef OVO_EMU
-        if (t < R) mbar_wait(&bar[t % kVsStrips], (t / kVsStrips) & 1);
+            mbar_wait(&bar[r % kVsStrips], (r / kVsStrips) & 1);
+#else
+            ovo_emu::spin_until(&emu_landed[r % kVsStrips], r);
 #endif
-        bool act[kVsSlots], mine[kVsSlots];
-        uint32_t c[kVsSlots][NPR];
+            uint32_t c[kVsSlots][NPR];
 #pragma unroll
-        for (int k = 0; k < kVsSlots; k++) {
-            const int r = t - sl[k].kind;
-            act[k] = !CHECK || (r >= 0 && r < R);
-            if (act[k]) {
-                OVO_DEVCHECK(sl[k].scol >= 0 && sl[k].scol + NPR <= SW * DH && sl[k].sbase == (r % kVsStrips) * SW * DH);
-                ldv<NPR>(c[k], strips + sl[k].sbase + sl[k].scol);
+            for (int k = 0; k < kVsSlots; k++) {
+                OVO_DEVCHECK(sl[k].scol >= 0 && sl[k].scol + NPR <= SW * DH && sbase == (r % kVsStrips) * SW * DH);
+                ldv<NPR>(c[k], strips + sbase + sl[k].scol);
             }
-        }
+            bool mine[kVsSlots];
 #pragma unroll
-        for (int k = 0; k < kVsSlots; k++) {
-            if (!act[k]) continue;
-            mine[k] = live[k] && (unsigned)(sl[k].scol - mine_lo) < (unsigned)(B * DH);
-            if (EDGE) {
-                const int xc = x[k] + (sl[k].dcol / DH) * (t - sl[k].kind);
-                // a diagonal line enters the image here: its predecessor lies outside (all-zero vector)
-                if (sl[k].dcol != 0 && xc == (sl[k].dcol > 0 ? 0 : W1 - 1)) path_reset<NPR>(sl[k].s);
-                mine[k] = mine[k] && xc < W1;
-            }
-            path_step<LPC, NPR, PAD>(sl[k].s, c[k], padmask, P1P1, P2P2, pl);
-        }
-#pragma unroll
-        for (int k = 0; k < kVsSlots; k++) {
-            if (!act[k]) continue;
-            if (mine[k]) {
-                OVO_DEVCHECK(sl[k].rbase == ((t - sl[k].kind) % kVsRing) * B * DH && sl[k].scol - mine_lo >= 0 &&
-                             sl[k].scol - mine_lo + DH - q * NPR <= B * DH);
-                OVO_DEVCHECK(sl[k].off >= 0 && (size_t)sl[k].off + NPR <= vol &&
-                             sl[k].off == (int32_t)(((ptrdiff_t)(y0 + t - sl[k].kind) * W1 + x[k] + (sl[k].dcol / DH) * (t - sl[k].kind)) * DH + q * NPR));
-                vs_meet<LPC, NPR, BR, SAT>(sl[k], q, ring, Sv);
-                if (CHECK && t - sl[k].kind == R - 1) {
-                    const int xc = x[k] + (sl[k].dcol / DH) * (R - 1);
-                    OVO_DEVCHECK(xc >= 0 && xc < W1);
-                    stv<NPR>(bb_out + ((size_t)sl[k].kind * W1 + xc) * DH + q * NPR, sl[k].s.L);
+            for (int k = 0; k < kVsSlots; k++) {
+                mine[k] = (unsigned)(sl[k].scol - mine_lo) < (unsigned)(B * DH);
+                if (EDGE && KIND != 0) {
+                    const int xc = sl[k].x + DX * r;
+                    // a diagonal line enters the image here: its predecessor lies outside (all-zero vector)
+                    if (xc == (DX > 0 ? 0 : W1 - 1)) path_reset<NPR>(sl[k].s);
+                    mine[k] = mine[k] && xc < W1;
+                } else if (EDGE) {
+                    mine[k] = mine[k] && sl[k].x < W1;
                 }
+                path_step<LPC, NPR, PAD>(sl[k].s, c[k], padmask, P1P1, P2P2, pl);
             }
-            vs_advance<LPC, NPR, BR, VG>(sl[k]);
+            if (KIND == 1) nbar_sync(1 + ri, NA);
+            if (KIND == 2) nbar_sync(1 + kVsRing + ri, NB);
+#pragma unroll
+            for (int k = 0; k < kVsSlots; k++) {
+                if (mine[k]) {
+                    OVO_DEVCHECK(rbase == (r % kVsRing) * B * DH && sl[k].scol - mine_lo >= 0 && sl[k].scol - mine_lo + DH - q * NPR <= B * DH);
+                    OVO_DEVCHECK(sl[k].off >= 0 && (size_t)sl[k].off + NPR <= vol &&
+                                 sl[k].off == (int32_t)(((ptrdiff_t)(y0 + r) * W1 + sl[k].x + DX * r) * DH + q * NPR));
+                    vs_meet<KIND, LPC, NPR, SAT>(sl[k].s, ring + rbase + (sl[k].scol - mine_lo), q, Sv + sl[k].off);
+                    if (r == R - 1) {
+                        const int xc = sl[k].x + DX * r;
+                        OVO_DEVCHECK(xc >= 0 && xc < W1);
+                        stv<NPR>(bb_out + ((size_t)KIND * W1 + xc) * DH + q * NPR, sl[k].s.L);
+                    }
+                }
+                sl[k].scol += DX * DH;
+                sl[k].off += (W1 + DX) * DH;
+            }
+            if (KIND == 0) nbar_arrive(1 + ri, NA);
+            if (KIND == 1) nbar_arrive(1 + kVsRing + ri, NB);
+            if (KIND == 2 && r + kVsRing < R) nbar_arrive(1 + 2 * kVsRing + ri, NC);  // (nobody waits for the band's last rows)
+            sbase = sbase == (kVsStrips - 1) * SW * DH ? 0 : sbase + SW * DH;
+            rbase = rbase == (kVsRing - 1) * B * DH ? 0 : rbase + B * DH;
+            ri = ri == kVsRing - 1 ? 0 : ri + 1;
         }
-        __syncthreads();
     };
     using T = std::true_type;
     using F = std::false_type;
-    int t = 0;
-    if (edge) {
-        for (; t < 2 && t < R + 2; t++) iteration(t, T(), T());
-        for (; t < R - 1; t++) iteration(t, F(), T());
-        for (; t < R + 2; t++) iteration(t, T(), T());
+    using K0 = std::integral_constant<int, 0>;
+    using K1 = std::integral_constant<int, 1>;
+    using K2 = std::integral_constant<int, 2>;
+    if (wid < WV) {
+        if (edge) run(K0(), T(), wid); else run(K0(), F(), wid);
+    } else if (wid < WV + WD) {
+        if (edge) run(K1(), T(), wid - WV); else run(K1(), F(), wid - WV);
     } else {
-        for (; t < 2 && t < R + 2; t++) iteration(t, T(), F());
-        for (; t < R - 1; t++) iteration(t, F(), F());  // rows 2 .. R-2: every slot is inside the band and away from its last row
-        for (; t < R + 2; t++) iteration(t, T(), F());
+        if (edge) run(K2(), T(), wid - WV - WD); else run(K2(), F(), wid - WV - WD);
     }
 }
 

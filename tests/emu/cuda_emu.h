@@ -71,7 +71,13 @@ struct Warp {
     int arrived = 0, alive = 0;
     unsigned gen = 0;
 };
+struct NamedBar {  // bar.arrive / bar.sync with an explicit thread count (producer / consumer hand-over)
+    int arrived = 0;
+    unsigned gen = 0;
+    std::vector<char> seen;
+};
 struct Engine {
+    NamedBar nbar[16];
     ucontext_t sched;
     std::vector<ucontext_t> ctx;
     std::vector<char> done;
@@ -113,7 +119,16 @@ inline void launch(dim3 grid, dim3 block, size_t smem, const std::function<void(
                 g_blockIdx = {bx, by, bz};
                 e.nthreads = e.live = nt;
                 e.bar_arrived = 0;
+                for (auto& nb : e.nbar) { nb.arrived = 0; nb.gen = 0; nb.seen.assign(nt, 0); }
                 e.warps.assign((nt + 31) / 32, Warp());
+                // OVO_EMU_POISON=<byte>: fill the thread stacks and the dynamic shared memory of every CTA with that byte, so that a
+                // read of an uninitialised local or shared-memory word gives the same (wrong) value every run instead of leftovers
+                static const char* poison = getenv("OVO_EMU_POISON");
+                if (poison) {
+                    const int pb = (int)strtol(poison, nullptr, 0);
+                    for (int t = 0; t < nt; t++) memset(e.stacks[t], pb, STK);
+                    memset(e.dyn_smem.data(), pb, e.dyn_smem.size() * 8);
+                }
                 for (int t = 0; t < nt; t++) {
                     e.done[t] = 0;
                     e.warps[t >> 5].alive++;
@@ -123,8 +138,20 @@ inline void launch(dim3 grid, dim3 block, size_t smem, const std::function<void(
                     e.ctx[t].uc_link = &e.sched;
                     makecontext(&e.ctx[t], (void (*)())trampoline, 0);
                 }
+                // OVO_EMU_SCHED: 0 / unset = round robin in thread order, 1 = reverse order, n >= 2 = pseudo-random order (seed n)
+                // reshuffled every sweep: other interleavings of the warps for kernels that synchronise by named barriers / flags
+                static const long sched_mode = getenv("OVO_EMU_SCHED") ? atol(getenv("OVO_EMU_SCHED")) : 0;
+                std::vector<int> order(nt);
+                for (int t = 0; t < nt; t++) order[t] = sched_mode == 1 ? nt - 1 - t : t;
+                uint64_t rng = 0x9E3779B97F4A7C15ull * (uint64_t)(sched_mode + 1);
                 while (e.live > 0)
-                    for (int t = 0; t < nt; t++) {
+                    for (int oi = 0; oi < nt; oi++) {
+                        if (sched_mode >= 2 && oi == 0)
+                            for (int i = nt - 1; i > 0; i--) {
+                                rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+                                std::swap(order[i], order[(rng >> 33) % (uint64_t)(i + 1)]);
+                            }
+                        const int t = order[oi];
                         if (e.done[t]) continue;
                         e.cur = t;
                         g_threadIdx = {(unsigned)(t % block.x), (unsigned)((t / block.x) % block.y), (unsigned)(t / (block.x * block.y))};
@@ -144,6 +171,33 @@ inline void block_barrier() {
     while (e.bar_gen == g) {
         yield();
         if (e.bar_gen == g && e.bar_arrived >= e.live) { e.bar_arrived = 0; e.bar_gen++; }
+    }
+}
+// named barrier: completes when `count` threads have arrived (arriving or waiting); a thread may not arrive twice in one phase
+// (on hardware that corrupts the phase), and a wait that never completes is a dead-lock: both abort the test
+inline void named_barrier(int id, int count, bool wait) {
+    Engine& e = eng();
+    NamedBar& b = e.nbar[id];
+    if (b.seen[e.cur]) { fprintf(stderr, "emu: thread %d arrives twice at named barrier %d\n", e.cur, id); abort(); }
+    b.seen[e.cur] = 1;
+    const unsigned g = b.gen;
+    if (++b.arrived >= count) {
+        b.arrived = 0;
+        b.gen++;
+        std::fill(b.seen.begin(), b.seen.end(), 0);
+        return;
+    }
+    if (!wait) return;
+    for (long spins = 0; b.gen == g; spins++) {
+        if (spins > 20000000) { fprintf(stderr, "emu: dead-lock at named barrier %d (thread %d)\n", id, e.cur); abort(); }
+        yield();
+    }
+}
+// wait (yielding) until a flag written by another thread has the expected value
+inline void spin_until(const volatile int* flag, int value) {
+    for (long spins = 0; *flag != value; spins++) {
+        if (spins > 20000000) { fprintf(stderr, "emu: dead-lock waiting for a flag (thread %d)\n", eng().cur); abort(); }
+        yield();
     }
 }
 // all live lanes of the warp deposit v; returns pointer to the 32 deposited values (valid until the next-but-one collective)

@@ -73,6 +73,22 @@ def test_sgbm_kernels_one_volume_per_direction(emu, monkeypatch):
     subprocess.run([sys.executable, "-c", code], check=True, env=dict(os.environ, OVO_SGBM_FUSED="0"))
 
 
+@pytest.mark.parametrize("sched", ["1", "5", "11"])
+def test_sgbm_kernels_other_warp_interleavings(emu, sched):
+    """The fused vertical kernel hands rows from warp to warp through producer / consumer named barriers and copy-engine flags, with
+    no CTA-wide barrier: its result must not depend on how the warps interleave.  OVO_EMU_SCHED runs the emulator's threads in
+    reverse / pseudo-random order (reshuffled every sweep) and OVO_EMU_POISON fills stacks and shared memory with a byte pattern;
+    both are read once per process, hence the child interpreter.  A thread arriving twice in one barrier phase or a wait that
+    never completes aborts the child."""
+    import subprocess
+    code = ("import sys; sys.path[:0] = [%r, %r, %r]; import test_emu_kernels as T, build_emu; from openvo_b200 import _native as N; "
+            "lib = N.load(build_emu.build()); T._sgbm_case(lib, 214, 70, 64, 1, dict(uniquenessRatio=5, _d=9)); "
+            "T._sgbm_case(lib, 265, 33, 128, 1, dict(_d=20)); T._sgbm_case(lib, 353, 17, 256, 1, dict(_d=40)); "
+            "T._sgbm_case(lib, 140, 18, 128, 1, dict(_d=3))"
+            % (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "emu")))
+    subprocess.run([sys.executable, "-c", code], check=True, env=dict(os.environ, OVO_EMU_SCHED=sched, OVO_EMU_POISON="0xA5"))
+
+
 def _sgbm_case(emu, W, H, D, nb, kw):
     kw = dict(kw)
     shift = kw.pop("_d", 7)
