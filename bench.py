@@ -577,7 +577,7 @@ def main():
                     "ms_per_launch": dur_s * 1e3, "share_of_step": prof[top][0] / tot,
                     "note": "kernel with the largest share of the step.  Since round 2 the path kernels write ONE vertical volume "
                             "(Sv) instead of three, which halves their algorithmic bytes; they are no longer HBM-bound (ncu: DRAM 29 % "
-                            "for k_sgbm_vsum, 55 % for k_sgbm_horiz) but limited by the ALU / DPX pipe and a barrier per row (48 % / 69 % pipe utilisation, "
+                            "for k_sgbm_vsum, 55 % for k_sgbm_horiz) but limited by the ALU / DPX pipe and shared-memory latency (46 % / 69 % pipe utilisation, "
                             "profiles/r02_ncu_full_summary.txt), so this HBM fraction is low by construction"}
     stages = None
     if rank == 0 and per_kernel:
